@@ -1,0 +1,166 @@
+"""torch custom ops over the C ABI (CUDA only, no autograd -- the reference never differentiates
+through its features: the extractor returns numpy, HF:models/whisper/feature_extraction_whisper.py:164).
+
+    torch.ops.b200mel.whisper_logmel(wave, lengths) -> (B, 80, 3000) float32
+    torch.ops.b200mel.whisper_frame_mask(lengths)   -> (B, 3000) int32
+    torch.ops.b200mel.mel_power(wave, log_eps)       -> (B, 64, 1 + T // 512) float32
+
+All inputs and outputs live on the same CUDA device; the kernels are enqueued on the current
+stream of that device without any host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+W_NMEL, W_NFRAME, W_NSAMP = 80, 3000, 480000
+U_NMEL, U_HOP, U_NFFT = 64, 512, 1024
+
+_handles: dict = {}
+_hlock = threading.Lock()
+
+
+def _handle(device: torch.device, preset: int) -> ctypes.c_void_p:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, preset)
+    h = _handles.get(key)
+    if h is None:
+        with _hlock:
+            h = _handles.get(key)
+            if h is None:
+                lib = _lib.load()
+                out = ctypes.c_void_p()
+                _lib.check(lib.b200mel_create(idx, preset, ctypes.byref(out)), "b200mel_create")
+                _handles[key] = h = out
+    return h
+
+
+def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"b200mel: `{name}` must be a CUDA tensor (this library has no CPU path)")
+
+
+_LIBDEF = torch.library.Library("b200mel", "DEF")
+_LIBDEF.define("whisper_logmel(Tensor wave, Tensor? lengths) -> Tensor")
+_LIBDEF.define("whisper_frame_mask(Tensor lengths) -> Tensor")
+_LIBDEF.define("mel_power(Tensor wave, float log_eps) -> Tensor")
+
+
+def _whisper_logmel_cuda(wave: torch.Tensor, lengths: Optional[torch.Tensor]) -> torch.Tensor:
+    _require_cuda(wave, "wave")
+    if wave.dim() != 2 or wave.dtype != torch.float32:
+        raise ValueError("b200mel.whisper_logmel: wave must be a (B, T) float32 tensor")
+    batch, t = wave.shape
+    if t % 4 != 0 or wave.stride(1) != 1 or wave.stride(0) % 4 != 0 or wave.data_ptr() % 16 != 0:
+        # keep the kernel's alignment contract: repack into a 16-byte aligned, stride%4==0 buffer
+        tp = (t + 3) // 4 * 4
+        if lengths is None:
+            lengths = torch.full((batch,), t, dtype=torch.int32, device=wave.device)
+        buf = torch.zeros((batch, tp), dtype=torch.float32, device=wave.device)
+        buf[:, :t] = wave
+        wave = buf
+    stride = wave.stride(0) if batch > 1 else wave.shape[1]
+    if lengths is not None:
+        _require_cuda(lengths, "lengths")
+        if lengths.dtype != torch.int32:
+            lengths = lengths.to(torch.int32)
+        lengths = lengths.contiguous()
+        if lengths.numel() != batch:
+            raise ValueError("b200mel.whisper_logmel: lengths must have one entry per clip")
+    out = torch.empty((batch, W_NMEL, W_NFRAME), dtype=torch.float32, device=wave.device)
+    if batch == 0:
+        return out
+    lib = _lib.load()
+    h = _handle(wave.device, _lib.PRESET_WHISPER)
+    ws_bytes = lib.b200mel_workspace_bytes(h, batch)
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=wave.device)
+    with torch.cuda.device(wave.device):
+        st = lib.b200mel_whisper_logmel_f32(
+            h, ctypes.c_void_p(wave.data_ptr()), stride,
+            ctypes.c_void_p(lengths.data_ptr()) if lengths is not None else None,
+            batch, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+            _stream_ptr(wave.device))
+    _lib.check(st, "b200mel_whisper_logmel_f32")
+    return out
+
+
+def _whisper_frame_mask_cuda(lengths: torch.Tensor) -> torch.Tensor:
+    _require_cuda(lengths, "lengths")
+    lengths = lengths.to(torch.int32).contiguous()
+    batch = lengths.numel()
+    out = torch.empty((batch, W_NFRAME), dtype=torch.int32, device=lengths.device)
+    if batch == 0:
+        return out
+    lib = _lib.load()
+    h = _handle(lengths.device, _lib.PRESET_WHISPER)
+    with torch.cuda.device(lengths.device):
+        st = lib.b200mel_whisper_frame_mask(h, ctypes.c_void_p(lengths.data_ptr()), batch,
+                                            ctypes.c_void_p(out.data_ptr()), _stream_ptr(lengths.device))
+    _lib.check(st, "b200mel_whisper_frame_mask")
+    return out
+
+
+def _mel_power_cuda(wave: torch.Tensor, log_eps: float) -> torch.Tensor:
+    _require_cuda(wave, "wave")
+    if wave.dim() != 2 or wave.dtype != torch.float32:
+        raise ValueError("b200mel.mel_power: wave must be a (B, T) float32 tensor")
+    batch, t = wave.shape
+    if t <= U_NFFT // 2:
+        raise ValueError(f"b200mel.mel_power: reflect padding needs more than {U_NFFT // 2} samples, got {t}")
+    if t % 4 != 0 or wave.stride(1) != 1 or wave.stride(0) % 4 != 0 or wave.data_ptr() % 16 != 0:
+        tp = (t + 3) // 4 * 4
+        buf = torch.zeros((batch, tp), dtype=torch.float32, device=wave.device)
+        buf[:, :t] = wave
+        wave = buf
+    stride = wave.stride(0) if batch > 1 else wave.shape[1]
+    out = torch.empty((batch, U_NMEL, 1 + t // U_HOP), dtype=torch.float32, device=wave.device)
+    if batch == 0:
+        return out
+    lib = _lib.load()
+    h = _handle(wave.device, _lib.PRESET_URBAN)
+    with torch.cuda.device(wave.device):
+        st = lib.b200mel_mel_f32(h, ctypes.c_void_p(wave.data_ptr()), stride, t, batch, float(log_eps),
+                                 ctypes.c_void_p(out.data_ptr()), _stream_ptr(wave.device))
+    _lib.check(st, "b200mel_mel_f32")
+    return out
+
+
+_LIBDEF.impl("whisper_logmel", _whisper_logmel_cuda, "CUDA")
+_LIBDEF.impl("whisper_frame_mask", _whisper_frame_mask_cuda, "CUDA")
+_LIBDEF.impl("mel_power", _mel_power_cuda, "CUDA")
+
+
+@torch.library.register_fake("b200mel::whisper_logmel")
+def _whisper_logmel_fake(wave, lengths):
+    return wave.new_empty((wave.shape[0], W_NMEL, W_NFRAME), dtype=torch.float32)
+
+
+@torch.library.register_fake("b200mel::whisper_frame_mask")
+def _whisper_frame_mask_fake(lengths):
+    return lengths.new_empty((lengths.shape[0], W_NFRAME), dtype=torch.int32)
+
+
+@torch.library.register_fake("b200mel::mel_power")
+def _mel_power_fake(wave, log_eps):
+    return wave.new_empty((wave.shape[0], U_NMEL, 1 + wave.shape[1] // U_HOP), dtype=torch.float32)
+
+
+def whisper_logmel(wave: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return torch.ops.b200mel.whisper_logmel(wave, lengths)
+
+
+def whisper_frame_mask(lengths: torch.Tensor) -> torch.Tensor:
+    return torch.ops.b200mel.whisper_frame_mask(lengths)
+
+
+def mel_power(wave: torch.Tensor, log_eps: float = -1.0) -> torch.Tensor:
+    return torch.ops.b200mel.mel_power(wave, log_eps)

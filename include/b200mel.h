@@ -1,0 +1,116 @@
+/*
+ * b200mel.h -- C ABI of libb200mel.so, the B200 (sm_100a) log-mel front end.
+ *
+ * This is the drop-in boundary for the one hot path this library replaces in
+ * k0r1g/audio-transformers.  The reference has no FFI of its own: the path is reached through
+ * two Python calls into third-party packages.  Each entry point below names the reference
+ * interface it stands in for (REF = reference tree, HF = transformers, TA = torchaudio):
+ *
+ *   b200mel_whisper_logmel_f32   HF:models/whisper/feature_extraction_whisper.py:135-164
+ *                                (_torch_extract_fbank_features) together with the pad/trim of
+ *                                HF:feature_extraction_sequence_utils.py:263-278,327-332, as
+ *                                invoked from REF:whisper_finetune/dataset.py:58-62 and
+ *                                REF:whisper_finetune/inference.py:154,200.
+ *   b200mel_whisper_frame_mask   HF:models/whisper/feature_extraction_whisper.py:328-337
+ *                                (attention-mask rescale).
+ *   b200mel_mel_f32              TA:transforms/_transforms.py:621-631 (MelSpectrogram.forward ->
+ *                                Spectrogram -> MelScale) plus REF:urban_sounds/dataset.py:56
+ *                                (torch.log(mel + 1e-9)), as built at REF:urban_sounds/dataset.py:19-24.
+ *   b200mel_get_table            the construction-time constants of both call sites
+ *                                (HF:audio_utils.py:453-544 mel_filter_bank; TA:functional/
+ *                                functional.py:518-587 melscale_fbanks; torch.hann_window).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers owned by the caller; 16-byte aligned.
+ *   - Every call is asynchronous and stream-ordered on `stream` (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream).  No host synchronisation, no allocation, so a
+ *     call may be captured into a CUDA graph.
+ *   - Return value: 0 on success, a negative b200mel_status otherwise.  The message for the
+ *     calling thread's last failure is available from b200mel_last_error().  Nothing throws or
+ *     exits across this boundary.
+ *   - A handle is immutable after creation; concurrent calls from several host threads or
+ *     streams are safe as long as each call uses its own workspace.
+ *   - There is no CPU path: on a machine without a compute-capability-10.x device
+ *     b200mel_create fails with B200MEL_ERR_UNSUPPORTED_ARCH / B200MEL_ERR_CUDA.
+ */
+#ifndef B200MEL_H_
+#define B200MEL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MEL_VERSION 100 /* 0.1.0 */
+
+typedef enum b200mel_status {
+  B200MEL_OK = 0,
+  B200MEL_ERR_BAD_ARG = -1,
+  B200MEL_ERR_BAD_ALIGN = -2,
+  B200MEL_ERR_CUDA = -3,
+  B200MEL_ERR_UNSUPPORTED_ARCH = -4,
+  B200MEL_ERR_WORKSPACE = -5
+} b200mel_status;
+
+typedef enum b200mel_preset {
+  B200MEL_PRESET_WHISPER = 0, /* 16 kHz, n_fft 400, hop 160, 80 Slaney mels, 480000 -> 3000 frames */
+  B200MEL_PRESET_URBAN = 1    /* 22.05 kHz, n_fft 1024, hop 512, 64 HTK mels, T -> 1 + T/512 frames */
+} b200mel_preset;
+
+typedef enum b200mel_table {
+  B200MEL_TABLE_WINDOW = 0,     /* n_fft floats, periodic Hann                                  */
+  B200MEL_TABLE_FILTERBANK = 1  /* dense (n_fft/2+1) x n_mels floats, row-major, bins x mels    */
+} b200mel_table;
+
+typedef struct b200mel_handle b200mel_handle;
+
+/* Library version (B200MEL_VERSION of the build). */
+int b200mel_version(void);
+
+/* Message describing the calling thread's most recent failure ("" if none). */
+const char* b200mel_last_error(void);
+
+/* Create a handle bound to CUDA device `device` for one preset.  Verifies the device is
+ * compute capability 10.x and configures the kernels (shared-memory carve-out, occupancy). */
+int b200mel_create(int device, int preset, b200mel_handle** out);
+int b200mel_destroy(b200mel_handle* h);
+
+/* Bytes of device workspace a call with `batch` clips needs (per-clip reduction slots and
+ * scheduler words).  The workspace needs no initialisation by the caller. */
+size_t b200mel_workspace_bytes(const b200mel_handle* h, int32_t batch);
+
+/* Whisper preset.
+ *   wave     [batch][stride_samples] float32; clip i holds lengths[i] valid samples (the rest is
+ *            never read).  stride_samples % 4 == 0.
+ *   lengths  [batch] int32 device array, or NULL meaning every clip has `stride_samples` samples.
+ *            Clips longer than 480000 samples are truncated, shorter ones are treated as
+ *            right-padded with zeros to 480000 (the extractor's padding="max_length").
+ *   out      [batch][80][3000] float32: (log10(max(mel,1e-10)) clamped to clip max - 8, + 4) / 4.
+ */
+int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples,
+                               const int32_t* lengths, int32_t batch, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* (B, 3000) int32 frame mask: mask[b][t] = (160*t < min(lengths[b], 480000)). */
+int b200mel_whisper_frame_mask(b200mel_handle* h, const int32_t* lengths, int32_t batch,
+                               int32_t* mask_out, void* stream);
+
+/* Urban preset.
+ *   wave      [batch][stride_samples] float32, n_samples valid samples per clip (n_samples >= 513,
+ *             reflect padding needs it), stride_samples % 4 == 0.
+ *   log_eps   >= 0: out = log(mel + log_eps) (natural log; the reference uses 1e-9);  < 0: out = mel.
+ *   out       [batch][64][1 + n_samples/512] float32.
+ */
+int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples, int32_t n_samples,
+                    int32_t batch, float log_eps, float* out, void* stream);
+
+/* Copy one of the preset's constant tables to HOST memory `dst` (capacity in floats).
+ * Returns the number of floats written, or a negative status. */
+int64_t b200mel_get_table(int preset, int table, float* dst, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MEL_H_ */

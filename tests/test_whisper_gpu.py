@@ -1,0 +1,137 @@
+"""GPU parity tests for the Whisper preset: CUDA path (through the torch custom op -> C ABI) vs the
+CPU oracle, the committed golden vectors and, when importable, the live HF extractor.
+
+Tolerance (BASELINE.md section 5 / north_star): max-abs <= 1e-4 on the normalised log-mel.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audio_transformers_b200 import signals
+from oracle import logmel_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from audio_transformers_b200 import ops as _ops
+    return _ops
+
+
+def _run(ops, clips, lengths=None):
+    """clips: list of 1-D float32 arrays (ragged).  Returns (B, 80, 3000) numpy."""
+    width = (max(len(c) for c in clips) + 3) // 4 * 4
+    host = np.zeros((len(clips), max(width, 4)), dtype=np.float32)
+    for i, c in enumerate(clips):
+        host[i, :len(c)] = c
+    wave = torch.from_numpy(host).cuda()
+    lens = torch.tensor([len(c) for c in clips] if lengths is None else lengths, dtype=torch.int32).cuda()
+    out = ops.whisper_logmel(wave, lens)
+    torch.cuda.synchronize()
+    assert out.shape == (len(clips), 80, 3000) and out.dtype == torch.float32 and out.is_cuda and out.is_contiguous()
+    return out.cpu().numpy()
+
+
+def test_golden_vectors(ops, golden_dir):
+    g = np.load(os.path.join(golden_dir, "whisper_golden.npz"))
+    names = [str(n) for n in g["names"]]
+    report = {}
+    for name in names:
+        index, length = (int(v) for v in g[f"{name}/meta"])
+        wav = signals.whisper_clip(index, seed=0, n_samples=length, kind=str(g[f"{name}/kind"]))
+        out = _run(ops, [wav])[0]
+        frames, values, stats = g[f"{name}/frames"], g[f"{name}/values"], g[f"{name}/stats"]
+        err = float(np.abs(out[:, frames] - values).max())
+        report[name] = err
+        assert np.isfinite(out).all()
+        assert err <= TOL, (name, err)
+        assert abs(float(out.max()) - stats[1]) <= TOL and abs(float(out.min()) - stats[2]) <= TOL, name
+    print("max-abs vs golden:", {k: f"{v:.2e}" for k, v in report.items()})
+
+
+def test_signal_classes_vs_oracle(ops):
+    """Per signal class, against the FP32 oracle (contract) and the FP64 restatement (truth)."""
+    clips = [signals.whisper_clip(i, seed=11) for i in range(8)]           # 2 of each class
+    out = _run(ops, clips)
+    ref32 = O.whisper_logmel(clips, dtype=np.float32)
+    ref64 = O.whisper_logmel(clips, dtype=np.float64)
+    for i in range(8):
+        e32 = float(np.abs(out[i] - ref32[i]).max())
+        e64 = float(np.abs(out[i] - ref64[i]).max())
+        print(f"class {signals.CLASSES[i % 4]:10s} |cuda-oracle32| {e32:.2e}  |cuda-oracle64| {e64:.2e}")
+        assert e32 <= TOL and e64 <= TOL
+
+
+def test_ragged_and_edge_lengths(ops):
+    lengths = list(signals.EDGE_LENGTHS) + [int(v) for v in signals.ragged_lengths(5, seed=1)]
+    clips = [signals.whisper_clip(100 + i, seed=2, n_samples=L) for i, L in enumerate(lengths)]
+    out = _run(ops, clips)
+    ref = O.whisper_logmel(clips, dtype=np.float32)
+    assert np.abs(out - ref).max() <= TOL
+    # clips longer than 30 s are truncated exactly like the extractor does
+    long = clips[lengths.index(600000)]
+    assert np.array_equal(out[lengths.index(600000)], _run(ops, [long[:480000]])[0])
+
+
+def test_zeros_and_floor(ops):
+    out = _run(ops, [np.zeros(480000, np.float32), np.zeros(7, np.float32)])
+    assert np.abs(out + 1.5).max() < 1e-6                                      # (-10 + 4) / 4
+
+
+def test_lengths_none_means_full_stride(ops):
+    clips = signals.whisper_batch(3, seed=5)
+    wave = torch.from_numpy(clips).cuda()
+    a = ops.whisper_logmel(wave, None).cpu().numpy()
+    b = _run(ops, list(clips))
+    assert np.array_equal(a, b)
+    assert np.abs(a - O.whisper_logmel(list(clips))).max() <= TOL
+
+
+def test_segment_chunks_like_inference(ops):
+    """REF:whisper_finetune/inference.py:176-200: a 30 s clip cut into six 5 s chunks, each padded to 30 s."""
+    clip = signals.whisper_clip(1, seed=9)
+    chunks = [clip[i * 80000:(i + 1) * 80000] for i in range(6)]
+    out = _run(ops, chunks)
+    ref = O.whisper_logmel(chunks)
+    assert np.abs(out - ref).max() <= TOL
+
+
+def test_batch_independence_and_determinism(ops):
+    clips = [signals.whisper_clip(i, seed=4) for i in range(5)]
+    a = _run(ops, clips)
+    b = _run(ops, clips[::-1])[::-1]
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, _run(ops, clips))
+
+
+def test_live_hf_extractor(ops):
+    tr = pytest.importorskip("transformers")
+    fe = tr.WhisperFeatureExtractor()
+    clips = [signals.whisper_clip(i, seed=21, n_samples=n) for i, n in enumerate((480000, 123457, 480000, 32000))]
+    ref = fe([c.astype(np.float64) for c in clips], sampling_rate=16000, return_tensors="pt").input_features.numpy()
+    out = _run(ops, clips)
+    err = np.abs(out - ref).reshape(len(clips), -1).max(axis=1)
+    print("max-abs vs live HF per clip:", err)
+    assert err.max() <= TOL
+
+
+def test_frame_mask(ops):
+    lens = torch.tensor([1, 160, 161, 480000, 600000], dtype=torch.int32).cuda()
+    m = ops.whisper_frame_mask(lens).cpu().numpy()
+    assert np.array_equal(m, O.whisper_attention_mask([1, 160, 161, 480000, 600000]))
+
+
+def test_unaligned_inputs_are_repacked(ops):
+    clip = signals.whisper_clip(2, seed=6, n_samples=100003)
+    wave = torch.from_numpy(clip[None, :]).cuda()                              # T % 4 != 0
+    out = ops.whisper_logmel(wave, None).cpu().numpy()
+    assert np.abs(out - O.whisper_logmel([clip])).max() <= TOL
+
+
+def test_cpu_tensor_fails_loudly(ops):
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ops.whisper_logmel(torch.zeros(1, 480000), None)
