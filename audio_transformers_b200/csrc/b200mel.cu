@@ -35,6 +35,12 @@ namespace host_tab {                      // host copies, so table queries need 
 }  // namespace host_tab
 #include "fft_codelets.cuh"
 
+// runtime (warp-uniform) lookups of the sparse filter structure from the constant bank
+__constant__ int c_wmel_len[80] = kWMelLen_INIT;
+__constant__ int c_wmel_off[80] = kWMelOff_INIT;
+__device__ __forceinline__ int kWMelLenDev(int m) { return c_wmel_len[m]; }
+__device__ __forceinline__ int kWMelOffDev(int m) { return c_wmel_off[m]; }
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -47,170 +53,191 @@ constexpr int W_THREADS = 256;
 constexpr int W_WARPS = W_THREADS / 32;
 constexpr int W_SPAN = (W_TILE - 1) * W_HOP + W_NFFT;            // 5360 samples staged per tile
 constexpr int W_PITCH = W_HOP + 1;                               // 161: odd pitch -> conflict-free lanes
-constexpr int W_ROWS = (W_SPAN + W_HOP - 1) / W_HOP;             // 34
-constexpr int W_SM_AUDIO = W_ROWS * W_PITCH;                     // floats
-constexpr int W_SM_E = 400 * 32;
-constexpr int W_SM_P = 201 * 32;
-constexpr int W_SMEM_BYTES = (W_SM_AUDIO + W_SM_E + W_SM_P + 32) * 4;
+constexpr int W_ROWS = (W_SPAN + W_HOP - 1) / W_HOP;             // 34 rows (last one half full)
+constexpr int W_SM_AUDIO = ((W_ROWS * W_PITCH + 31) / 32) * 32;  // floats per audio buffer
+constexpr int W_EROWS = 16 * 26;                                 // 16 classes x 13 complex outputs
+constexpr int W_SM_E = W_EROWS * 32;
+constexpr int W_SMEM_BYTES = (W_SM_E + 2 * W_SM_AUDIO) * 4;
 
 // y = (log10(e) + 4) / 4 = log2(e) * (log10(2)/4) + 1
 __device__ __forceinline__ float w_norm_log(float e) {
   return __fmaf_rn(__log2f(e), 0.07525749891599529f, 1.0f);
 }
 
-// ---- pass 1: windowed real 25-point DFT for residue class A ---------------------------------
-template <int A>
-__device__ __forceinline__ void w_pass1(const float* __restrict__ audio_lane, float* __restrict__ e_lane) {
-  float x[25], w[25], o[25];
-#pragma unroll
-  for (int b = 0; b < 25; ++b) {
-    const int n = b2::pfa400_n(A, b);
-    x[b] = audio_lane[(n / W_HOP) * W_PITCH + (n % W_HOP)];
-    w[b] = c_win400[n];
-  }
-  b2::real_dft25(x, w, o);
-#pragma unroll
-  for (int c = 0; c < 25; ++c) e_lane[(A * 25 + c) * 32] = o[c];
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
 }
 
-// ---- pass 2: complex 16-point DFT for k2 = K2, power into P ----------------------------------
-template <int K2>
-__device__ __forceinline__ void w_pass2(const float* __restrict__ e_lane, float* __restrict__ p_lane) {
+// ---- stage one tile of audio into shared memory ------------------------------------------------
+// Row r of the tile holds samples [160 r, 160 r + 160) at pitch 161.  Interior tiles stream with
+// cp.async (4-byte granularity: the odd pitch is what makes the 32 frame-lanes conflict free, and it
+// rules out 16-byte destinations); tiles touching a clip edge take the generic path that applies the
+// reflect padding of the 480000-sample padded clip and the zero fill past the clip length.
+__device__ __forceinline__ void w_stage(const float* __restrict__ src, int L, int f0, float* __restrict__ s_audio,
+                                        int warp, int lane) {
+  const int g0 = f0 * W_HOP - W_NFFT / 2;
+  const bool interior = (g0 >= 0) && (g0 + W_ROWS * W_HOP <= L);
+  if (interior) {
+    for (int r = warp; r < W_ROWS; r += W_WARPS) {
+      const float* g = src + g0 + r * W_HOP + lane;
+      float* d = s_audio + r * W_PITCH + lane;
+#pragma unroll
+      for (int k = 0; k < W_HOP / 32; ++k) cp_async4(d + 32 * k, g + 32 * k);
+    }
+  } else {
+    for (int r = warp; r < W_ROWS; r += W_WARPS) {
+#pragma unroll
+      for (int k = 0; k < W_HOP / 32; ++k) {
+        const int g = g0 + r * W_HOP + lane + 32 * k;
+        const int j = g < 0 ? -g : (g >= W_NSAMP ? 2 * (W_NSAMP - 1) - g : g);
+        s_audio[r * W_PITCH + lane + 32 * k] = (j < L) ? __ldg(src + j) : 0.0f;
+      }
+    }
+  }
+}
+
+// ---- pass 1: windowed real 25-point DFT of residue class `a` (warp-uniform, runtime) -------------
+// Input order and window taps come from the constant tables c_wp1_off / c_wp1_win, so one code body
+// serves all 16 classes (the fully specialised variant was instruction-cache bound, profiles/r01_v1).
+__device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_lane, float* __restrict__ e_lane) {
+  float x[25], w[25], o[25];
+  const int* __restrict__ off = c_wp1_off + a * 28;
+  const float* __restrict__ win = c_wp1_win + a * 28;
+#pragma unroll
+  for (int b = 0; b < 25; ++b) {
+    x[b] = audio_lane[off[b]];
+    w[b] = win[b];
+  }
+  b2::real_dft25(x, w, o);
+  float* dst = e_lane + a * (26 * 32);
+  dst[0] = o[0];
+  dst[32] = 0.0f;                       // Im X0 = 0 keeps pass 2 free of special cases
+#pragma unroll
+  for (int c = 1; c < 25; ++c) dst[(c + 1) * 32] = o[c];
+}
+
+// ---- pass 2: complex 16-point DFT for k2 (warp-uniform, runtime); |X|^2 written back in place ----
+__device__ __forceinline__ void w_pass2(int k2, float* __restrict__ e_lane) {
   float yr[16], yi[16], Xr[16], Xi[16];
+  float* base = e_lane + k2 * 64;       // rows a*26 + 2*k2 (re) and a*26 + 2*k2 + 1 (im)
 #pragma unroll
   for (int a = 0; a < 16; ++a) {
-    if (K2 == 0) { yr[a] = e_lane[(a * 25) * 32]; yi[a] = 0.0f; }
-    else { yr[a] = e_lane[(a * 25 + 2 * K2 - 1) * 32]; yi[a] = e_lane[(a * 25 + 2 * K2) * 32]; }
+    yr[a] = base[a * (26 * 32)];
+    yi[a] = base[a * (26 * 32) + 32];
   }
   b2::cplx_dft16(yr, yi, Xr, Xi);
 #pragma unroll
-  for (int k1 = 0; k1 < (K2 == 0 ? 9 : 16); ++k1)
-    p_lane[b2::pfa400_bin(k1, K2) * 32] = __fmaf_rn(Xr[k1], Xr[k1], Xi[k1] * Xi[k1]);
+  for (int k1 = 0; k1 < 16; ++k1) base[k1 * (26 * 32)] = __fmaf_rn(Xr[k1], Xr[k1], Xi[k1] * Xi[k1]);
 }
 
-// constexpr views of the generated sparse-filter tables, callable in device constant expressions
-B2_CX int w_mel_start(int m) { const int t[80] = kWMelStart_INIT; return t[m]; }
-B2_CX int w_mel_len(int m) { const int t[80] = kWMelLen_INIT; return t[m]; }
-B2_CX int w_mel_off(int m) { const int t[80] = kWMelOff_INIT; return t[m]; }
-
-// ---- mel: one filter -----------------------------------------------------------------------------
-template <int M>
-__device__ __forceinline__ void w_mel_one(const float* __restrict__ p_lane, float* __restrict__ out_row,
-                                          bool valid, float& emax) {
-  constexpr int START = w_mel_start(M), LEN = w_mel_len(M), OFF = w_mel_off(M);
+// ---- mel: one filter with LEN taps -----------------------------------------------------------------
+template <int LEN>
+__device__ __forceinline__ float w_mel_dot(const float* __restrict__ p_lane, int off) {
   float acc = 0.0f;
 #pragma unroll
-  for (int j = 0; j < LEN; ++j)
-    acc = __fmaf_rn(p_lane[(START + j) * 32], c_wmelw[OFF + j], acc);
-  const float e = fmaxf(acc, 1e-10f);
-  if (valid) {
-    emax = fmaxf(emax, e);
-    out_row[(size_t)M * W_NFRAME] = w_norm_log(e);
-  }
+  for (int j = 0; j < LEN; ++j) acc = __fmaf_rn(p_lane[c_wmel_row[off + j]], c_wmelw[off + j], acc);
+  return acc;
 }
 
-template <int W>
-__device__ __forceinline__ void w_mel_warp(const float* p_lane, float* out_row, bool valid, float& emax) {
-  w_mel_one<W + 0>(p_lane, out_row, valid, emax);  w_mel_one<W + 8>(p_lane, out_row, valid, emax);
-  w_mel_one<W + 16>(p_lane, out_row, valid, emax); w_mel_one<W + 24>(p_lane, out_row, valid, emax);
-  w_mel_one<W + 32>(p_lane, out_row, valid, emax); w_mel_one<W + 40>(p_lane, out_row, valid, emax);
-  w_mel_one<W + 48>(p_lane, out_row, valid, emax); w_mel_one<W + 56>(p_lane, out_row, valid, emax);
-  w_mel_one<W + 64>(p_lane, out_row, valid, emax); w_mel_one<W + 72>(p_lane, out_row, valid, emax);
+__device__ __forceinline__ float w_mel(const float* __restrict__ p_lane, int m) {
+  const int len = kWMelLenDev(m), off = kWMelOffDev(m);
+  switch (len) {
+    case 1: return w_mel_dot<1>(p_lane, off);
+    case 2: return w_mel_dot<2>(p_lane, off);
+    case 3: return w_mel_dot<3>(p_lane, off);
+    case 4: return w_mel_dot<4>(p_lane, off);
+    case 5: return w_mel_dot<5>(p_lane, off);
+    case 6: return w_mel_dot<6>(p_lane, off);
+    case 7: return w_mel_dot<7>(p_lane, off);
+    case 8: return w_mel_dot<8>(p_lane, off);
+    case 9: return w_mel_dot<9>(p_lane, off);
+    case 10: return w_mel_dot<10>(p_lane, off);
+    case 11: return w_mel_dot<11>(p_lane, off);
+    case 12: return w_mel_dot<12>(p_lane, off);
+    case 13: return w_mel_dot<13>(p_lane, off);
+    default: return w_mel_dot<14>(p_lane, off);
+  }
 }
 
 __global__ void __launch_bounds__(W_THREADS, 2)
 whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
                       int batch, float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
   extern __shared__ __align__(16) float smem[];
-  float* s_audio = smem;
-  float* s_e = s_audio + W_SM_AUDIO;
-  float* s_p = s_e + W_SM_E;
-  float* s_red = s_p + W_SM_P;
+  float* s_e = smem;
+  float* s_audio0 = smem + W_SM_E;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int clip = blockIdx.x / W_TILES_PER_CLIP;
-  const int tile = blockIdx.x - clip * W_TILES_PER_CLIP;
-  const int f0 = tile * W_TILE;
-  if (clip >= batch) return;
+  const int ntiles = batch * W_TILES_PER_CLIP;
 
-  // ---- stage audio (reflect pad at both ends of the 480000-sample padded clip, zeros past L) ----
-  {
-    long long len_ll = lengths ? (long long)lengths[clip] : stride;
-    const int L = (int)(len_ll < 0 ? 0 : (len_ll > W_NSAMP ? W_NSAMP : len_ll));
-    const float* __restrict__ src = wave + (size_t)clip * (size_t)stride;
-    const int g0 = f0 * W_HOP - W_NFFT / 2;
-#pragma unroll 4
-    for (int s = tid; s < W_SPAN; s += W_THREADS) {
-      int g = g0 + s;
-      int j = g < 0 ? -g : (g >= W_NSAMP ? 2 * (W_NSAMP - 1) - g : g);
-      float v = (j < L) ? __ldg(src + j) : 0.0f;
-      s_audio[(s / W_HOP) * W_PITCH + (s % W_HOP)] = v;
-    }
+  auto clip_len = [&](int clip) {
+    long long len_ll = lengths ? (long long)__ldg(lengths + clip) : stride;
+    return (int)(len_ll < 0 ? 0 : (len_ll > W_NSAMP ? W_NSAMP : len_ll));
+  };
+
+  int tile = blockIdx.x;
+  if (tile < ntiles) {
+    const int clip = tile / W_TILES_PER_CLIP;
+    w_stage(wave + (size_t)clip * (size_t)stride, clip_len(clip), (tile - clip * W_TILES_PER_CLIP) * W_TILE,
+            s_audio0, warp, lane);
   }
-  __syncthreads();
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int clip = tile / W_TILES_PER_CLIP;
+    const int f0 = (tile - clip * W_TILES_PER_CLIP) * W_TILE;
+    float* s_audio = s_audio0 + (it & 1) * W_SM_AUDIO;
 
-  // ---- pass 1 ---------------------------------------------------------------------------------
-  {
-    const float* al = s_audio + lane * W_PITCH;
-    float* el = s_e + lane;
-    switch (warp) {
-      case 0: w_pass1<0>(al, el); w_pass1<8>(al, el); break;
-      case 1: w_pass1<1>(al, el); w_pass1<9>(al, el); break;
-      case 2: w_pass1<2>(al, el); w_pass1<10>(al, el); break;
-      case 3: w_pass1<3>(al, el); w_pass1<11>(al, el); break;
-      case 4: w_pass1<4>(al, el); w_pass1<12>(al, el); break;
-      case 5: w_pass1<5>(al, el); w_pass1<13>(al, el); break;
-      case 6: w_pass1<6>(al, el); w_pass1<14>(al, el); break;
-      default: w_pass1<7>(al, el); w_pass1<15>(al, el); break;
-    }
-  }
-  __syncthreads();
+    cp_async_commit_wait_all();
+    __syncthreads();                       // audio(tile) visible; E is free (previous mel finished)
 
-  // ---- pass 2 ---------------------------------------------------------------------------------
-  {
-    const float* el = s_e + lane;
-    float* pl = s_p + lane;
-    switch (warp) {
-      case 0: w_pass2<1>(el, pl); w_pass2<9>(el, pl); break;
-      case 1: w_pass2<2>(el, pl); w_pass2<10>(el, pl); break;
-      case 2: w_pass2<3>(el, pl); w_pass2<11>(el, pl); break;
-      case 3: w_pass2<4>(el, pl); w_pass2<12>(el, pl); break;
-      case 4: w_pass2<5>(el, pl); w_pass2<0>(el, pl); break;
-      case 5: w_pass2<6>(el, pl); break;
-      case 6: w_pass2<7>(el, pl); break;
-      default: w_pass2<8>(el, pl); break;
+    {                                      // prefetch the next tile's audio into the other buffer
+      const int next = tile + gridDim.x;
+      if (next < ntiles) {
+        const int nclip = next / W_TILES_PER_CLIP;
+        w_stage(wave + (size_t)nclip * (size_t)stride, clip_len(nclip), (next - nclip * W_TILES_PER_CLIP) * W_TILE,
+                s_audio0 + ((it + 1) & 1) * W_SM_AUDIO, warp, lane);
+      }
     }
-  }
-  __syncthreads();
 
-  // ---- mel + log + per-clip max ---------------------------------------------------------------
-  {
-    const int frame = f0 + lane;
-    const bool valid = frame < W_NFRAME;
-    const float* pl = s_p + lane;
-    float* out_row = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame;
-    float emax = 0.0f;
-    switch (warp) {
-      case 0: w_mel_warp<0>(pl, out_row, valid, emax); break;
-      case 1: w_mel_warp<1>(pl, out_row, valid, emax); break;
-      case 2: w_mel_warp<2>(pl, out_row, valid, emax); break;
-      case 3: w_mel_warp<3>(pl, out_row, valid, emax); break;
-      case 4: w_mel_warp<4>(pl, out_row, valid, emax); break;
-      case 5: w_mel_warp<5>(pl, out_row, valid, emax); break;
-      case 6: w_mel_warp<6>(pl, out_row, valid, emax); break;
-      default: w_mel_warp<7>(pl, out_row, valid, emax); break;
+    // ---- pass 1: 16 tasks over 8 warps ---------------------------------------------------------
+    {
+      const float* al = s_audio + lane * W_PITCH;
+      float* el = s_e + lane;
+#pragma unroll 1
+      for (int a = warp; a < 16; a += W_WARPS) w_pass1(a, al, el);
     }
+    __syncthreads();
+
+    // ---- pass 2: 13 tasks over 8 warps ---------------------------------------------------------
+    {
+      float* el = s_e + lane;
+#pragma unroll 1
+      for (int k2 = warp; k2 < 13; k2 += W_WARPS) w_pass2(k2, el);
+    }
+    __syncthreads();
+
+    // ---- mel + log + per-clip max ----------------------------------------------------------------
+    {
+      const int frame = f0 + lane;
+      const bool valid = frame < W_NFRAME;
+      const float* pl = s_e + lane;
+      float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame;
+      float emax = 0.0f;
+#pragma unroll 1
+      for (int m = warp; m < W_NMEL; m += W_WARPS) {
+        const float e = fmaxf(w_mel(pl, m), 1e-10f);
+        if (valid) {
+          emax = fmaxf(emax, e);
+          out_col[(size_t)m * W_NFRAME] = w_norm_log(e);
+        }
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
-    if (lane == 0) s_red[warp] = emax;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    float m = s_red[0];
-#pragma unroll
-    for (int w = 1; w < W_WARPS; ++w) m = fmaxf(m, s_red[w]);
-    // positive floats order like their bit patterns; the slot is zeroed before the launch
-    atomicMax(clip_max_bits + clip, __float_as_uint(m));
+      for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+      // positive floats order like their bit patterns; the slot is zeroed before the launch
+      if (lane == 0 && emax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(emax));
+    }
   }
 }
 
@@ -259,6 +286,11 @@ struct b200mel_handle {
   int device;
   int preset;
   int sm_count;
+  // optional benchmark instrumentation (b200mel_profile_begin/end)
+  bool prof_on = false;
+  int prof_cap = 0, prof_n = 0;
+  cudaEvent_t* prof_ev = nullptr;   // 2 * prof_cap events
+  b200mel_handle(int d, int p, int s) : device(d), preset(p), sm_count(s) {}
 };
 
 extern "C" {
@@ -289,13 +321,49 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
     e = cudaFuncSetAttribute(whisper_logmel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaSetDevice(prev);
   if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute");
-  b200mel_handle* h = new b200mel_handle{device, preset, prop.multiProcessorCount};
+  b200mel_handle* h = new b200mel_handle(device, preset, prop.multiProcessorCount);
   *out = h;
   return B200MEL_OK;
 }
 
+static void prof_free(b200mel_handle* h) {
+  if (h->prof_ev) {
+    for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev;
+  }
+  h->prof_ev = nullptr; h->prof_cap = 0; h->prof_n = 0; h->prof_on = false;
+}
+
 int b200mel_destroy(b200mel_handle* h) {
+  if (h) prof_free(h);
   delete h;
+  return B200MEL_OK;
+}
+
+int b200mel_profile_begin(b200mel_handle* h, int32_t max_launches) {
+  if (!h || max_launches <= 0) return fail(B200MEL_ERR_BAD_ARG, "profile_begin: bad handle or max_launches");
+  prof_free(h);
+  h->prof_ev = new cudaEvent_t[2 * (size_t)max_launches];
+  for (int i = 0; i < 2 * max_launches; ++i) {
+    cudaError_t e = cudaEventCreate(&h->prof_ev[i]);
+    if (e != cudaSuccess) { h->prof_cap = i / 2; prof_free(h); return fail_cuda(e, "cudaEventCreate"); }
+  }
+  h->prof_cap = max_launches; h->prof_n = 0; h->prof_on = true;
+  return B200MEL_OK;
+}
+
+int b200mel_profile_end(b200mel_handle* h, double* total_ms, int32_t* launches) {
+  if (!h || !total_ms || !launches) return fail(B200MEL_ERR_BAD_ARG, "profile_end: NULL argument");
+  double sum = 0.0;
+  for (int i = 0; i < h->prof_n; ++i) {
+    cudaError_t e = cudaEventSynchronize(h->prof_ev[2 * i + 1]);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]);
+    if (e != cudaSuccess) { prof_free(h); return fail_cuda(e, "profile_end"); }
+    sum += ms;
+  }
+  *total_ms = sum; *launches = h->prof_n;
+  prof_free(h);
   return B200MEL_OK;
 }
 
@@ -322,8 +390,13 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   unsigned int* clip_max = (unsigned int*)workspace;
   cudaError_t e = cudaMemsetAsync(clip_max, 0, (size_t)batch * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
-  whisper_logmel_kernel<<<batch * W_TILES_PER_CLIP, W_THREADS, W_SMEM_BYTES, stream>>>(
+  const int ntiles = batch * W_TILES_PER_CLIP;
+  const int grid_main = ntiles < 2 * h->sm_count ? ntiles : 2 * h->sm_count;   // persistent: 2 CTAs per SM
+  const bool prof = h->prof_on && h->prof_n < h->prof_cap;
+  if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
+  whisper_logmel_kernel<<<grid_main, W_THREADS, W_SMEM_BYTES, stream>>>(
       wave, (long long)stride_samples, lengths, batch, out, clip_max);
+  if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "whisper_logmel_kernel launch");
   dim3 grid(30, batch);

@@ -164,3 +164,17 @@ def whisper_frame_mask(lengths: torch.Tensor) -> torch.Tensor:
 
 def mel_power(wave: torch.Tensor, log_eps: float = -1.0) -> torch.Tensor:
     return torch.ops.b200mel.mel_power(wave, log_eps)
+
+
+def profile_begin(device, preset: int = _lib.PRESET_WHISPER, max_launches: int = 4096) -> None:
+    """Benchmark hook: bracket the dominant kernel of every following call with CUDA events."""
+    dev = torch.device(device)
+    _lib.check(_lib.load().b200mel_profile_begin(_handle(dev, preset), max_launches), "b200mel_profile_begin")
+
+
+def profile_end(device, preset: int = _lib.PRESET_WHISPER):
+    """Returns (summed dominant-kernel milliseconds, launches covered)."""
+    dev = torch.device(device)
+    ms, n = ctypes.c_double(0.0), ctypes.c_int32(0)
+    _lib.check(_lib.load().b200mel_profile_end(_handle(dev, preset), ctypes.byref(ms), ctypes.byref(n)), "b200mel_profile_end")
+    return ms.value, n.value

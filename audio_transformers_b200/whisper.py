@@ -189,6 +189,11 @@ class B200WhisperFeatureExtractor:
             if wave.dtype != torch.float32:
                 wave = wave.to(torch.float32)
             dev_lengths = lengths.to(dev) if lengths is not None else None
+        elif (isinstance(raw_speech, torch.Tensor) and raw_speech.dim() == 2 and raw_speech.dtype == torch.float32
+              and raw_speech.is_contiguous()):
+            # new: an already collated host batch (ideally pinned): one asynchronous H2D, no restaging
+            wave = raw_speech.to(dev, non_blocking=True)
+            dev_lengths = lengths.to(dev, non_blocking=True) if lengths is not None else None
         else:
             if isinstance(raw_speech, torch.Tensor):
                 raw_speech = raw_speech.numpy()

@@ -106,6 +106,15 @@ int b200mel_whisper_frame_mask(b200mel_handle* h, const int32_t* lengths, int32_
 int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples, int32_t n_samples,
                     int32_t batch, float log_eps, float* out, void* stream);
 
+/* Optional per-kernel timing for benchmarks: between profile_begin and profile_end every call on
+ * this handle brackets its dominant kernel (the fused log-mel kernel, not the memset / clamp pass)
+ * with a pair of CUDA events recorded on the call's stream, up to `max_launches` pairs.
+ * profile_end waits for the recorded events, returns the summed kernel time in milliseconds and the
+ * number of launches covered, and switches profiling off again.  Not CUDA-graph capturable and not
+ * thread-safe; leave it off in production. */
+int b200mel_profile_begin(b200mel_handle* h, int32_t max_launches);
+int b200mel_profile_end(b200mel_handle* h, double* total_ms, int32_t* launches);
+
 /* Copy one of the preset's constant tables to HOST memory `dst` (capacity in floats).
  * Returns the number of floats written, or a negative status. */
 int64_t b200mel_get_table(int preset, int table, float* dst, int64_t capacity);
