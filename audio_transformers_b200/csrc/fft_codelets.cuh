@@ -242,6 +242,87 @@ B2_HD void cplx_dft16(const V yr[16], const V yi[16], V Xr[16], V Xi[16]) {
   }
 }
 
+// multiply (r + i m) by exp(-2 pi i E / 32), E compile-time (even E reuse the /16 table)
+#define B2_C32_1 0.98078528040323044913
+#define B2_S32_1 0.19509032201612826785
+#define B2_C32_3 0.83146961230254523708
+#define B2_S32_3 0.55557023301960222474
+template <int E, class V>
+B2_HD void twiddle32(V& r, V& m) {
+  typedef typename real_t<V>::type R;
+  constexpr int e = ((E % 32) + 32) % 32;
+  if (e % 2 == 0) { twiddle16<e / 2>(r, m); return; }
+  // odd e: angle = e * 11.25 deg; fold into the first octant
+  R c = 0, s = 0;
+  if (e == 1)  { c = (R)B2_C32_1;  s = (R)B2_S32_1; }
+  if (e == 3)  { c = (R)B2_C32_3;  s = (R)B2_S32_3; }
+  if (e == 5)  { c = (R)B2_S32_3;  s = (R)B2_C32_3; }
+  if (e == 7)  { c = (R)B2_S32_1;  s = (R)B2_C32_1; }
+  if (e == 9)  { c = (R)-B2_S32_1; s = (R)B2_C32_1; }
+  if (e == 11) { c = (R)-B2_S32_3; s = (R)B2_C32_3; }
+  if (e == 13) { c = (R)-B2_C32_3; s = (R)B2_S32_3; }
+  if (e == 15) { c = (R)-B2_C32_1; s = (R)B2_S32_1; }
+  if (e > 16)  {   // W^(e) = -W^(e-16)
+    constexpr int f = e - 16;
+    if (f == 1)  { c = (R)-B2_C32_1; s = (R)-B2_S32_1; }
+    if (f == 3)  { c = (R)-B2_C32_3; s = (R)-B2_S32_3; }
+    if (f == 5)  { c = (R)-B2_S32_3; s = (R)-B2_C32_3; }
+    if (f == 7)  { c = (R)-B2_S32_1; s = (R)-B2_C32_1; }
+    if (f == 9)  { c = (R)B2_S32_1;  s = (R)-B2_C32_1; }
+    if (f == 11) { c = (R)B2_S32_3;  s = (R)-B2_C32_3; }
+    if (f == 13) { c = (R)B2_C32_3;  s = (R)-B2_S32_3; }
+    if (f == 15) { c = (R)B2_C32_1;  s = (R)-B2_S32_1; }
+  }
+  V nr = vfmac(m, s, vmulc(r, c));       // (c - i s)(r + i m) = (c r + s m) + i (c m - s r)
+  V nm = vfmac(r, -s, vmulc(m, c));
+  r = nr; m = nm;
+}
+
+template <int K, class V>
+B2_HD void dft32_combine(const V Er[16], const V Ei[16], const V Or[16], const V Oi[16], V Xr[32], V Xi[32]) {
+  V tr = Or[K], ti = Oi[K];
+  twiddle32<K>(tr, ti);
+  Xr[K] = vadd(Er[K], tr);      Xi[K] = vadd(Ei[K], ti);
+  Xr[K + 16] = vsub(Er[K], tr); Xi[K + 16] = vsub(Ei[K], ti);
+  if constexpr (K + 1 < 16) dft32_combine<K + 1>(Er, Ei, Or, Oi, Xr, Xi);
+}
+
+// ---- 32-point complex DFT: radix 2 x 16 (decimation in time) -----------------------------------
+template <class V>
+B2_HD void cplx_dft32(const V zr[32], const V zi[32], V Xr[32], V Xi[32]) {
+  V er[16], ei[16], orr[16], oi[16], Er[16], Ei[16], Or[16], Oi[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { er[j] = zr[2 * j]; ei[j] = zi[2 * j]; orr[j] = zr[2 * j + 1]; oi[j] = zi[2 * j + 1]; }
+  cplx_dft16(er, ei, Er, Ei);
+  cplx_dft16(orr, oi, Or, Oi);
+  dft32_combine<0>(Er, Ei, Or, Oi, Xr, Xi);
+}
+
+template <int K, class V>
+B2_HD void rdft32_untangle(const V Zr[16], const V Zi[16], V Xr[17], V Xi[17]) {
+  // X[k] = A + W32^k * B,  A = (Z[k] + conj Z[16-k]) / 2,  B = (Z[k] - conj Z[16-k]) / (2i)
+  typedef typename real_t<V>::type R;
+  constexpr int K2 = (16 - K) % 16;
+  V ar = vmulc(vadd(Zr[K], Zr[K2]), (R)0.5), ai = vmulc(vsub(Zi[K], Zi[K2]), (R)0.5);
+  V br = vmulc(vadd(Zi[K], Zi[K2]), (R)0.5), bi = vmulc(vsub(Zr[K2], Zr[K]), (R)0.5);
+  twiddle32<K>(br, bi);
+  Xr[K] = vadd(ar, br); Xi[K] = vadd(ai, bi);
+  if constexpr (K + 1 < 16) rdft32_untangle<K + 1>(Zr, Zi, Xr, Xi);
+}
+
+// ---- 32-point DFT of REAL (windowed) input, outputs k = 0..16 -----------------------------------
+// Packs z[j] = x[2j] + i x[2j+1], one complex 16-point DFT, then the standard untangling step.
+template <class V, class W>
+B2_HD void real_dft32(const V x[32], const W w[32], V Xr[17], V Xi[17]) {
+  V zr[16], zi[16], Zr[16], Zi[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { zr[j] = vmulc(x[2 * j], w[2 * j]); zi[j] = vmulc(x[2 * j + 1], w[2 * j + 1]); }
+  cplx_dft16(zr, zi, Zr, Zi);
+  rdft32_untangle<0>(Zr, Zi, Xr, Xi);
+  Xr[16] = vsub(Zr[0], Zi[0]);           // X[16] = sum_even - sum_odd (real)
+  Xi[16] = vsub(Zr[0], Zr[0]);           // exact zero of the right type
+}
+
 // ---- Good-Thomas index maps for N = 400 = 16 x 25 ----------------------------------------------
 B2_CX int pfa400_n(int a, int b) { return (25 * a + 16 * b) % 400; }
 B2_CX int pfa400_k(int k1, int k2) { return (225 * k1 + 176 * k2) % 400; }

@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/b200mel.h declares, serves its constant tables without a device, and refuses to compute
+without one (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from audio_transformers_b200 import build, _lib
+    build.build()                      # no-op when up to date; nvcc cross-compiles without a GPU
+    return _lib.load()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200mel.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200mel_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_library_agree(lib):
+    from audio_transformers_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 11
+    assert sorted(_lib.SYMBOLS) == declared          # the ctypes table binds exactly what the header declares
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in b200mel.h but not exported by libb200mel.so"
+    assert lib.b200mel_version() == 100
+
+
+def test_tables_match_reference_libraries(lib, golden_dir):
+    from audio_transformers_b200 import _lib
+    g = np.load(os.path.join(golden_dir, "tables.npz"))
+    assert np.array_equal(_lib.get_table(_lib.PRESET_WHISPER, _lib.TABLE_WINDOW), g["whisper_window"])
+    assert np.array_equal(_lib.get_table(_lib.PRESET_WHISPER, _lib.TABLE_FILTERBANK), g["whisper_mel_filters"].astype(np.float32))
+    assert np.array_equal(_lib.get_table(_lib.PRESET_URBAN, _lib.TABLE_WINDOW), g["urban_window"])
+    assert np.array_equal(_lib.get_table(_lib.PRESET_URBAN, _lib.TABLE_FILTERBANK), g["urban_fb"])
+    # REF:whisper_finetune/experiments.ipynb:563-569, straight from the library's own table
+    fb = _lib.get_table(_lib.PRESET_WHISPER, _lib.TABLE_FILTERBANK)
+    assert abs(float(fb[1, 0]) - 0.02486259) < 5e-9 and abs(float(fb[199, 79]) - 0.00044876) < 5e-9
+
+
+def test_error_reporting(lib):
+    buf = (ctypes.c_float * 4)()
+    n = lib.b200mel_get_table(0, 0, buf, 4)            # capacity too small
+    assert n == -1 and b"capacity" in lib.b200mel_last_error()
+    assert lib.b200mel_get_table(7, 0, buf, 4) == -1 and b"preset" in lib.b200mel_last_error()
+    out = ctypes.c_void_p()
+    assert lib.b200mel_create(0, 9, ctypes.byref(out)) == -1
+    assert lib.b200mel_workspace_bytes(None, 64) == 0
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    out = ctypes.c_void_p()
+    st = lib.b200mel_create(0, 0, ctypes.byref(out))
+    assert st in (-3, -4) and not out.value             # CUDA error / unsupported arch, never a CPU handle
+    from audio_transformers_b200 import B200MelSpectrogram, B200WhisperFeatureExtractor, ops
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ops.whisper_logmel(torch.zeros(1, 480000), None)
+    with pytest.raises(RuntimeError):
+        B200WhisperFeatureExtractor()(np.zeros(16000, np.float32), sampling_rate=16000, return_tensors="pt")
+    with pytest.raises(RuntimeError):
+        B200MelSpectrogram()(torch.zeros(1, 88200))
+
+
+def test_meta_shapes():
+    import torch
+    from audio_transformers_b200 import ops  # noqa: F401  (registers the ops)
+    w = torch.empty(5, 480000, device="meta")
+    assert torch.ops.b200mel.whisper_logmel(w, None).shape == (5, 80, 3000)
+    assert torch.ops.b200mel.mel_power(torch.empty(3, 88200, device="meta"), 1e-9).shape == (3, 64, 173)
+    assert torch.ops.b200mel.whisper_frame_mask(torch.empty(4, dtype=torch.int32, device="meta")).shape == (4, 3000)

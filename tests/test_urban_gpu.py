@@ -1,0 +1,101 @@
+"""GPU parity tests for the urban preset (MelSpectrogram(22050, 1024, hop 512, 64 mels) + log(.+1e-9)).
+
+Tolerance: max-abs <= 1e-4 on log(mel + 1e-9); the linear mel is checked
+relative to the clip's peak mel value.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audio_transformers_b200 import signals
+from oracle import logmel_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from audio_transformers_b200 import ops as _ops
+    return _ops
+
+
+def test_golden_vectors(ops, golden_dir):
+    g = np.load(os.path.join(golden_dir, "urban_golden.npz"))
+    wave = signals.urban_batch(int(g["batch"]), seed=int(g["seed"]))                  # (4, 1, 88200)
+    x = torch.from_numpy(wave[:, 0]).cuda()
+    logmel = ops.mel_power(x, 1e-9).cpu().numpy()
+    mel = ops.mel_power(x, -1.0).cpu().numpy()
+    assert logmel.shape == (4, 64, 173) and logmel.dtype == np.float32
+    err = float(np.abs(logmel - g["logmel"][:, 0]).max())
+    print(f"urban max-abs vs golden log-mel: {err:.2e}")
+    assert err <= TOL
+    assert np.abs(mel - g["mel"][:, 0]).max() <= 1e-5 * np.abs(g["mel"]).max()
+    z = ops.mel_power(torch.zeros(1, 88200, device="cuda"), 1e-9).cpu().numpy()
+    assert np.abs(z - g["zeros_logmel"][:, 0]).max() < 1e-5
+
+
+def test_config1_batch32_vs_oracle(ops):
+    """randn(32, 1, 88200) peak-normalised."""
+    wave = signals.urban_batch(32, seed=0)
+    out = ops.mel_power(torch.from_numpy(wave[:, 0]).cuda(), 1e-9).cpu().numpy()
+    ref32 = O.urban_melspec(wave, dtype=np.float32)[:, 0]
+    ref64 = O.urban_melspec(wave, dtype=np.float64)[:, 0]
+    e32, e64 = float(np.abs(out - ref32).max()), float(np.abs(out - ref64).max())
+    print(f"urban batch 32: |cuda-oracle32| {e32:.2e}  |cuda-oracle64| {e64:.2e}")
+    assert e32 <= TOL and e64 <= TOL
+
+
+@pytest.mark.parametrize("n", [88200, 513, 1000, 1024, 4096, 44100, 100003, 16384 + 512 * 31])
+def test_lengths(ops, n):
+    rng = np.random.default_rng(n)
+    wave = (0.3 * rng.standard_normal((3, n))).astype(np.float32)
+    wave[1] = (0.5 * np.sin(2 * np.pi * 1000.0 * np.arange(n) / 22050.0)).astype(np.float32)
+    x = torch.from_numpy(wave).cuda()
+    out = ops.mel_power(x, 1e-9).cpu().numpy()
+    ref = O.urban_melspec(wave, dtype=np.float32)
+    assert out.shape == ref.shape == (3, 64, 1 + n // 512)
+    # broadband clips: the contract tolerance on log(mel + 1e-9)
+    assert np.abs(out[[0, 2]] - ref[[0, 2]]).max() <= TOL
+    # pure tone: far-off mels sit at the FP32 round-off floor (~1e-14 of the peak power), below the 1e-9
+    # epsilon, where any two FP32 FFTs (including torch's own on different hardware) disagree in the log.
+    # Check the linear mel against the FP64 restatement relative to the clip's peak, and the log where the
+    # mel is comfortably above that floor.
+    lin = ops.mel_power(x, -1.0).cpu().numpy()[1]
+    lin64 = O.urban_melspec(wave[1:2], log_eps=None, dtype=np.float64)[0]
+    assert np.abs(lin - lin64).max() <= 1e-6 * lin64.max()
+    strong = lin64 > 1e-4 * lin64.max()
+    assert np.abs(out[1][strong] - np.log(lin64[strong] + 1e-9)).max() <= TOL
+
+
+def test_module_matches_live_torchaudio(ops):
+    ta = pytest.importorskip("torchaudio")
+    from audio_transformers_b200 import B200MelSpectrogram
+    ref_tf = ta.transforms.MelSpectrogram(sample_rate=22050, n_fft=1024, hop_length=512, n_mels=64)
+    mine = B200MelSpectrogram(sample_rate=22050, n_fft=1024, hop_length=512, n_mels=64)
+    assert set(mine.state_dict().keys()) == set(ref_tf.state_dict().keys()) == {"spectrogram.window", "mel_scale.fb"}
+    for k, v in ref_tf.state_dict().items():
+        assert torch.equal(v, mine.state_dict()[k]), k
+    wave = torch.from_numpy(signals.urban_batch(6, seed=3))                              # (6, 1, 88200)
+    ref = torch.log(ref_tf(wave) + 1e-9)
+    out = torch.log(mine(wave.cuda()) + 1e-9)                                           # REF:urban_sounds/dataset.py:55-56
+    assert out.shape == ref.shape == (6, 1, 64, 173) and out.is_cuda
+    assert (out.cpu() - ref).abs().max().item() <= TOL
+    fused = B200MelSpectrogram(log_eps=1e-9)(wave.cuda())
+    assert (fused.cpu() - ref).abs().max().item() <= TOL
+    # a single (1, T) clip, as REF:urban_sounds/dataset.py:55 passes it
+    one = mine(wave[0].cuda())
+    assert one.shape == (1, 64, 173)
+    assert torch.equal(one, mine(wave.cuda())[0])
+
+
+def test_errors(ops):
+    from audio_transformers_b200 import B200MelSpectrogram
+    with pytest.raises(NotImplementedError):
+        B200MelSpectrogram(n_mels=128)
+    with pytest.raises(RuntimeError):
+        B200MelSpectrogram()(torch.zeros(1, 88200))
+    with pytest.raises(ValueError):
+        ops.mel_power(torch.zeros(1, 512, device="cuda"), 1e-9)
