@@ -35,33 +35,32 @@ namespace host_tab {                      // host copies, so table queries need 
 }  // namespace host_tab
 #include "fft_codelets.cuh"
 
-// runtime (warp-uniform) lookups of the sparse filter structure from the constant bank
-__constant__ int c_wmel_len[80] = kWMelLen_INIT;
-__constant__ int c_wmel_off[80] = kWMelOff_INIT;
-__device__ __forceinline__ int kWMelLenDev(int m) { return c_wmel_len[m]; }
-__device__ __forceinline__ int kWMelOffDev(int m) { return c_wmel_off[m]; }
-
 namespace {
 
 // ------------------------------------------------------------------------------------------------
 // Whisper geometry
 // ------------------------------------------------------------------------------------------------
 constexpr int W_NFFT = 400, W_HOP = 160, W_NMEL = 80, W_NSAMP = 480000, W_NFRAME = 3000;
-constexpr int W_TILE = 32;                                       // frames per CTA tile (one per lane)
-constexpr int W_TILES_PER_CLIP = (W_NFRAME + W_TILE - 1) / W_TILE;   // 94
-constexpr int W_THREADS = 256;
-constexpr int W_WARPS = W_THREADS / 32;
-constexpr int W_SPAN = (W_TILE - 1) * W_HOP + W_NFFT;            // 5360 samples staged per tile
+constexpr int W_TILE = 64;                                       // frames per CTA tile: TWO per lane (packed f32x2)
+constexpr int W_TILES_PER_CLIP = (W_NFRAME + W_TILE - 1) / W_TILE;   // 47
+constexpr int W_THREADS = 512;
+constexpr int W_WARPS = W_THREADS / 32;                          // 16 = number of pass-1 tasks
+constexpr int W_P2_TASKS = 13;                                   // warps 0..12 run pass 2, warps 13..15 prefetch audio
+constexpr int W_SPAN = (W_TILE - 1) * W_HOP + W_NFFT;            // 10480 samples staged per tile
 constexpr int W_PITCH = W_HOP + 1;                               // 161: odd pitch -> conflict-free lanes
-constexpr int W_ROWS = (W_SPAN + W_HOP - 1) / W_HOP;             // 34 rows (last one half full)
-constexpr int W_SM_AUDIO = ((W_ROWS * W_PITCH + 31) / 32) * 32;  // floats per audio buffer
+constexpr int W_ROWS = (W_SPAN + W_HOP - 1) / W_HOP;             // 66 rows (last one half full)
+constexpr int W_SM_AUDIO = ((W_ROWS * W_PITCH + 31) / 32) * 32;  // floats
 constexpr int W_EROWS = 16 * 26;                                 // 16 classes x 13 complex outputs
-constexpr int W_SM_E = W_EROWS * 32;
-constexpr int W_SMEM_BYTES = (W_SM_E + 2 * W_SM_AUDIO) * 4;
+constexpr int W_SM_E = W_EROWS * 32 * 2;                         // floats (float2 per lane and row)
+constexpr int W_SM_TAB = 2 * 16 * 28;                            // pass-1 offsets (int) + window taps (float)
+constexpr int W_SMEM_BYTES = (W_SM_E + W_SM_AUDIO + W_SM_TAB) * 4;
+constexpr int W_LANE2 = 32 * W_PITCH;                            // float offset of a lane's second frame (f0 + 32 + lane)
 
-// y = (log10(e) + 4) / 4 = log2(e) * (log10(2)/4) + 1
+// y = (log10(e) + 4) / 4 = log2(e) * (log10(2)/4) + 1; e >= 1e-10 so the ftz approx form is exact enough
 __device__ __forceinline__ float w_norm_log(float e) {
-  return __fmaf_rn(__log2f(e), 0.07525749891599529f, 1.0f);
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(e));
+  return __fmaf_rn(l, 0.07525749891599529f, 1.0f);
 }
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
@@ -77,53 +76,73 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // cp.async (4-byte granularity: the odd pitch is what makes the 32 frame-lanes conflict free, and it
 // rules out 16-byte destinations); tiles touching a clip edge take the generic path that applies the
 // reflect padding of the 480000-sample padded clip and the zero fill past the clip length.
+// `part`/`nparts`: the rows are split over the warps that take part in the copy.
 __device__ __forceinline__ void w_stage(const float* __restrict__ src, int L, int f0, float* __restrict__ s_audio,
-                                        int warp, int lane) {
+                                        int part, int nparts, int lane) {
   const int g0 = f0 * W_HOP - W_NFFT / 2;
   const bool interior = (g0 >= 0) && (g0 + W_ROWS * W_HOP <= L);
   if (interior) {
-    for (int r = warp; r < W_ROWS; r += W_WARPS) {
-      const float* g = src + g0 + r * W_HOP + lane;
-      float* d = s_audio + r * W_PITCH + lane;
+    const float* g = src + g0 + part * W_HOP + lane;
+    float* d = s_audio + part * W_PITCH + lane;
+#pragma unroll 2
+    for (int r = part; r < W_ROWS; r += nparts) {
 #pragma unroll
       for (int k = 0; k < W_HOP / 32; ++k) cp_async4(d + 32 * k, g + 32 * k);
+      g += nparts * W_HOP;
+      d += nparts * W_PITCH;
     }
   } else {
-    for (int r = warp; r < W_ROWS; r += W_WARPS) {
+    for (int r = part; r < W_ROWS; r += nparts) {
 #pragma unroll
       for (int k = 0; k < W_HOP / 32; ++k) {
         const int g = g0 + r * W_HOP + lane + 32 * k;
         const int j = g < 0 ? -g : (g >= W_NSAMP ? 2 * (W_NSAMP - 1) - g : g);
-        s_audio[r * W_PITCH + lane + 32 * k] = (j < L) ? __ldg(src + j) : 0.0f;
+        s_audio[r * W_PITCH + lane + 32 * k] = (j >= 0 && j < L) ? __ldg(src + j) : 0.0f;
       }
     }
   }
 }
 
-// ---- pass 1: windowed real 25-point DFT of residue class `a` (warp-uniform, runtime) -------------
-// Input order and window taps come from the constant tables c_wp1_off / c_wp1_win, so one code body
-// serves all 16 classes (the fully specialised variant was instruction-cache bound, profiles/r01_v1).
-__device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_lane, float* __restrict__ e_lane) {
-  float x[25], w[25], o[25];
-  const int* __restrict__ off = c_wp1_off + a * 28;
-  const float* __restrict__ win = c_wp1_win + a * 28;
+// ---- pass 1: windowed real 25-point DFT of residue class a (warp-uniform) ----------------------
+// Good-Thomas input order and window taps come from tables (one code body for all 16 classes: a fully
+// specialised variant was instruction-cache bound, profiles/r01_v1).  The tables are read from a
+// shared-memory copy with broadcast 128-bit loads: register-indexed constant loads (LDC) of the same
+// data were the top stall of the previous version (profiles/r01_v4).  Each lane carries two frames
+// (f0 + lane, f0 + 32 + lane) as a packed float2.
+__device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_lane, float2* __restrict__ e_lane,
+                                        const int* __restrict__ s_off, const float* __restrict__ s_win) {
+  float2 x[25], o[25];
+  int off[28];
+  float w[28];
+  const int4* off4 = reinterpret_cast<const int4*>(s_off + a * 28);
+  const float4* win4 = reinterpret_cast<const float4*>(s_win + a * 28);
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const int4 v = off4[q];
+    off[4 * q] = v.x; off[4 * q + 1] = v.y; off[4 * q + 2] = v.z; off[4 * q + 3] = v.w;
+  }
 #pragma unroll
   for (int b = 0; b < 25; ++b) {
-    x[b] = audio_lane[off[b]];
-    w[b] = win[b];
+    const float* p = audio_lane + off[b];
+    x[b] = make_float2(p[0], p[W_LANE2]);
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const float4 v = win4[q];
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
   }
   b2::real_dft25(x, w, o);
-  float* dst = e_lane + a * (26 * 32);
+  float2* dst = e_lane + a * (26 * 32);
   dst[0] = o[0];
-  dst[32] = 0.0f;                       // Im X0 = 0 keeps pass 2 free of special cases
+  dst[32] = make_float2(0.0f, 0.0f);    // Im X0 = 0 keeps pass 2 free of special cases
 #pragma unroll
   for (int c = 1; c < 25; ++c) dst[(c + 1) * 32] = o[c];
 }
 
 // ---- pass 2: complex 16-point DFT for k2 (warp-uniform, runtime); |X|^2 written back in place ----
-__device__ __forceinline__ void w_pass2(int k2, float* __restrict__ e_lane) {
-  float yr[16], yi[16], Xr[16], Xi[16];
-  float* base = e_lane + k2 * 64;       // rows a*26 + 2*k2 (re) and a*26 + 2*k2 + 1 (im)
+__device__ __forceinline__ void w_pass2(int k2, float2* __restrict__ e_lane) {
+  float2 yr[16], yi[16], Xr[16], Xi[16];
+  float2* base = e_lane + k2 * 64;      // rows a*26 + 2*k2 (re) and a*26 + 2*k2 + 1 (im)
 #pragma unroll
   for (int a = 0; a < 16; ++a) {
     yr[a] = base[a * (26 * 32)];
@@ -131,107 +150,115 @@ __device__ __forceinline__ void w_pass2(int k2, float* __restrict__ e_lane) {
   }
   b2::cplx_dft16(yr, yi, Xr, Xi);
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) base[k1 * (26 * 32)] = __fmaf_rn(Xr[k1], Xr[k1], Xi[k1] * Xi[k1]);
+  for (int k1 = 0; k1 < 16; ++k1) base[k1 * (26 * 32)] = b2::vfma(Xr[k1], Xr[k1], b2::vmul(Xi[k1], Xi[k1]));
 }
 
-// ---- mel: one filter with LEN taps -----------------------------------------------------------------
-template <int LEN>
-__device__ __forceinline__ float w_mel_dot(const float* __restrict__ p_lane, int off) {
-  float acc = 0.0f;
-#pragma unroll
-  for (int j = 0; j < LEN; ++j) acc = __fmaf_rn(p_lane[c_wmel_row[off + j]], c_wmelw[off + j], acc);
-  return acc;
-}
+// ---- mel: filters are specialised at compile time per warp (row offsets and weights are immediates) ----
+B2_CX int w_mel_len(int m) { const int t[80] = kWMelLen_INIT; return t[m]; }
+B2_CX int w_mel_off(int m) { const int t[80] = kWMelOff_INIT; return t[m]; }
+B2_CX int w_mel_row(int i) { const int t[B200MEL_W_NNZ] = kWMelRow_INIT; return t[i]; }
+B2_CX float w_mel_wt(int i) { const float t[B200MEL_W_NNZ] = kWMelW_INIT; return t[i]; }
 
-__device__ __forceinline__ float w_mel(const float* __restrict__ p_lane, int m) {
-  const int len = kWMelLenDev(m), off = kWMelOffDev(m);
-  switch (len) {
-    case 1: return w_mel_dot<1>(p_lane, off);
-    case 2: return w_mel_dot<2>(p_lane, off);
-    case 3: return w_mel_dot<3>(p_lane, off);
-    case 4: return w_mel_dot<4>(p_lane, off);
-    case 5: return w_mel_dot<5>(p_lane, off);
-    case 6: return w_mel_dot<6>(p_lane, off);
-    case 7: return w_mel_dot<7>(p_lane, off);
-    case 8: return w_mel_dot<8>(p_lane, off);
-    case 9: return w_mel_dot<9>(p_lane, off);
-    case 10: return w_mel_dot<10>(p_lane, off);
-    case 11: return w_mel_dot<11>(p_lane, off);
-    case 12: return w_mel_dot<12>(p_lane, off);
-    case 13: return w_mel_dot<13>(p_lane, off);
-    default: return w_mel_dot<14>(p_lane, off);
+template <int I, int END>
+__device__ __forceinline__ void w_mel_taps(const float2* __restrict__ p_lane, float2& acc) {
+  if constexpr (I < END) {
+    constexpr int row = w_mel_row(I);
+    constexpr float wt = w_mel_wt(I);
+    acc = b2::vfmac(p_lane[row * 32], wt, acc);
+    w_mel_taps<I + 1, END>(p_lane, acc);
   }
 }
 
-__global__ void __launch_bounds__(W_THREADS, 2)
+template <int M>
+__device__ __forceinline__ void w_mel_one(const float2* __restrict__ p_lane, float* __restrict__ out_col,
+                                          bool valid0, bool valid1, float& emax) {
+  constexpr int OFF = w_mel_off(M), LEN = w_mel_len(M);
+  float2 acc = make_float2(0.0f, 0.0f);
+  w_mel_taps<OFF, OFF + LEN>(p_lane, acc);
+  const float e0 = fmaxf(acc.x, 1e-10f), e1 = fmaxf(acc.y, 1e-10f);
+  if (valid0) { emax = fmaxf(emax, e0); out_col[(size_t)M * W_NFRAME] = w_norm_log(e0); }
+  if (valid1) { emax = fmaxf(emax, e1); out_col[(size_t)M * W_NFRAME + 32] = w_norm_log(e1); }
+}
+
+template <int W>
+__device__ __forceinline__ void w_mel_warp(const float2* __restrict__ p_lane, float* __restrict__ out_col,
+                                           bool valid0, bool valid1, float& emax) {
+  w_mel_one<W>(p_lane, out_col, valid0, valid1, emax);
+  w_mel_one<W + 16>(p_lane, out_col, valid0, valid1, emax);
+  w_mel_one<W + 32>(p_lane, out_col, valid0, valid1, emax);
+  w_mel_one<W + 48>(p_lane, out_col, valid0, valid1, emax);
+  w_mel_one<W + 64>(p_lane, out_col, valid0, valid1, emax);
+}
+
+__global__ void __launch_bounds__(W_THREADS, 1)
 whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
                       int batch, float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
   extern __shared__ __align__(16) float smem[];
-  float* s_e = smem;
-  float* s_audio0 = smem + W_SM_E;
+  float2* s_e = reinterpret_cast<float2*>(smem);
+  float* s_audio = smem + W_SM_E;
+  int* s_off = reinterpret_cast<int*>(smem + W_SM_E + W_SM_AUDIO);
+  float* s_win = smem + W_SM_E + W_SM_AUDIO + 16 * 28;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntiles = batch * W_TILES_PER_CLIP;
+  if (tid < 16 * 28) { s_off[tid] = c_wp1_off[tid]; s_win[tid] = c_wp1_win[tid]; }
 
   auto clip_len = [&](int clip) {
     long long len_ll = lengths ? (long long)__ldg(lengths + clip) : stride;
     return (int)(len_ll < 0 ? 0 : (len_ll > W_NSAMP ? W_NSAMP : len_ll));
   };
+  auto stage_tile = [&](int t, int part, int nparts) {
+    const int c = t / W_TILES_PER_CLIP;
+    w_stage(wave + (size_t)c * (size_t)stride, clip_len(c), (t - c * W_TILES_PER_CLIP) * W_TILE, s_audio, part, nparts, lane);
+  };
 
   int tile = blockIdx.x;
-  if (tile < ntiles) {
-    const int clip = tile / W_TILES_PER_CLIP;
-    w_stage(wave + (size_t)clip * (size_t)stride, clip_len(clip), (tile - clip * W_TILES_PER_CLIP) * W_TILE,
-            s_audio0, warp, lane);
-  }
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+  if (tile < ntiles) stage_tile(tile, warp, W_WARPS);
+
+  for (; tile < ntiles; tile += gridDim.x) {
     const int clip = tile / W_TILES_PER_CLIP;
     const int f0 = (tile - clip * W_TILES_PER_CLIP) * W_TILE;
-    float* s_audio = s_audio0 + (it & 1) * W_SM_AUDIO;
 
     cp_async_commit_wait_all();
     __syncthreads();                       // audio(tile) visible; E is free (previous mel finished)
 
-    {                                      // prefetch the next tile's audio into the other buffer
+    // ---- pass 1: 16 tasks, one per warp ---------------------------------------------------------
+    w_pass1(warp, s_audio + lane * W_PITCH, s_e + lane, s_off, s_win);
+    __syncthreads();                       // E complete; the audio tile is dead from here on
+
+    // ---- pass 2: 13 tasks on warps 0..12; warps 13..15 prefetch the next tile's audio meanwhile ----
+    if (warp < W_P2_TASKS) {
+      w_pass2(warp, s_e + lane);
+    } else {
       const int next = tile + gridDim.x;
-      if (next < ntiles) {
-        const int nclip = next / W_TILES_PER_CLIP;
-        w_stage(wave + (size_t)nclip * (size_t)stride, clip_len(nclip), (next - nclip * W_TILES_PER_CLIP) * W_TILE,
-                s_audio0 + ((it + 1) & 1) * W_SM_AUDIO, warp, lane);
-      }
-    }
-
-    // ---- pass 1: 16 tasks over 8 warps ---------------------------------------------------------
-    {
-      const float* al = s_audio + lane * W_PITCH;
-      float* el = s_e + lane;
-#pragma unroll 1
-      for (int a = warp; a < 16; a += W_WARPS) w_pass1(a, al, el);
-    }
-    __syncthreads();
-
-    // ---- pass 2: 13 tasks over 8 warps ---------------------------------------------------------
-    {
-      float* el = s_e + lane;
-#pragma unroll 1
-      for (int k2 = warp; k2 < 13; k2 += W_WARPS) w_pass2(k2, el);
+      if (next < ntiles) stage_tile(next, warp - W_P2_TASKS, W_WARPS - W_P2_TASKS);
     }
     __syncthreads();
 
     // ---- mel + log + per-clip max ----------------------------------------------------------------
     {
-      const int frame = f0 + lane;
-      const bool valid = frame < W_NFRAME;
-      const float* pl = s_e + lane;
-      float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame;
+      const int frame0 = f0 + lane, frame1 = f0 + 32 + lane;
+      const bool valid0 = frame0 < W_NFRAME, valid1 = frame1 < W_NFRAME;
+      const float2* pl = s_e + lane;
+      float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame0;
       float emax = 0.0f;
-#pragma unroll 1
-      for (int m = warp; m < W_NMEL; m += W_WARPS) {
-        const float e = fmaxf(w_mel(pl, m), 1e-10f);
-        if (valid) {
-          emax = fmaxf(emax, e);
-          out_col[(size_t)m * W_NFRAME] = w_norm_log(e);
-        }
+      switch (warp) {
+        case 0: w_mel_warp<0>(pl, out_col, valid0, valid1, emax); break;
+        case 1: w_mel_warp<1>(pl, out_col, valid0, valid1, emax); break;
+        case 2: w_mel_warp<2>(pl, out_col, valid0, valid1, emax); break;
+        case 3: w_mel_warp<3>(pl, out_col, valid0, valid1, emax); break;
+        case 4: w_mel_warp<4>(pl, out_col, valid0, valid1, emax); break;
+        case 5: w_mel_warp<5>(pl, out_col, valid0, valid1, emax); break;
+        case 6: w_mel_warp<6>(pl, out_col, valid0, valid1, emax); break;
+        case 7: w_mel_warp<7>(pl, out_col, valid0, valid1, emax); break;
+        case 8: w_mel_warp<8>(pl, out_col, valid0, valid1, emax); break;
+        case 9: w_mel_warp<9>(pl, out_col, valid0, valid1, emax); break;
+        case 10: w_mel_warp<10>(pl, out_col, valid0, valid1, emax); break;
+        case 11: w_mel_warp<11>(pl, out_col, valid0, valid1, emax); break;
+        case 12: w_mel_warp<12>(pl, out_col, valid0, valid1, emax); break;
+        case 13: w_mel_warp<13>(pl, out_col, valid0, valid1, emax); break;
+        case 14: w_mel_warp<14>(pl, out_col, valid0, valid1, emax); break;
+        default: w_mel_warp<15>(pl, out_col, valid0, valid1, emax); break;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
@@ -517,7 +544,7 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   cudaError_t e = cudaMemsetAsync(clip_max, 0, (size_t)batch * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
   const int ntiles = batch * W_TILES_PER_CLIP;
-  const int grid_main = ntiles < 2 * h->sm_count ? ntiles : 2 * h->sm_count;   // persistent: 2 CTAs per SM
+  const int grid_main = ntiles < h->sm_count ? ntiles : h->sm_count;   // persistent: one 512-thread CTA per SM
   const bool prof = h->prof_on && h->prof_n < h->prof_cap;
   if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
   whisper_logmel_kernel<<<grid_main, W_THREADS, W_SMEM_BYTES, stream>>>(

@@ -58,6 +58,20 @@ B2_HD double vfmsc(double a, double c, double b) { return a * c - b; }
 B2_HD double vmul(double a, double b) { return a * b; }
 B2_HD double vfma(double a, double b, double c) { return a * b + c; }
 
+// packed pair of FP32 values (two frames per lane): Blackwell's FADD2 / FMUL2 / FFMA2 process both
+// halves in one issue slot and accept a scalar immediate / uniform register broadcast to both halves
+// and a negate modifier, so the packed codelets cost exactly half the issue slots of the scalar ones.
+#if defined(__CUDACC__)
+__device__ __forceinline__ float2 vneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 vsub(float2 a, float2 b) { return __fadd2_rn(a, vneg(b)); }
+__device__ __forceinline__ float2 vmulc(float2 a, float c) { return __fmul2_rn(a, make_float2(c, c)); }
+__device__ __forceinline__ float2 vfmac(float2 a, float c, float2 b) { return __ffma2_rn(a, make_float2(c, c), b); }
+__device__ __forceinline__ float2 vfmsc(float2 a, float c, float2 b) { return __ffma2_rn(a, make_float2(c, c), vneg(b)); }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+
 // ---- constants ---------------------------------------------------------------------------------
 #define B2_C5_1 0.30901699437494742410    // cos(2 pi / 5)
 #define B2_C5_2 (-0.80901699437494742410) // cos(4 pi / 5)
