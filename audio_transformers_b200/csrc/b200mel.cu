@@ -190,6 +190,13 @@ __device__ __forceinline__ void w_mel_warp(const float2* __restrict__ p_lane, fl
   w_mel_one<W + 64>(p_lane, out_col, valid0, valid1, emax);
 }
 
+#ifdef W_TRACE
+__device__ long long* g_trace = nullptr;     // [iter][4 marks][16 warps] clock64 of CTA 0 (debug builds only)
+#define W_MARK(k) do { if (blockIdx.x == 0 && lane == 0 && it < 32 && g_trace) g_trace[(it * 4 + (k)) * 16 + warp] = clock64(); } while (0)
+#else
+#define W_MARK(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(W_THREADS, 1)
 whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
                       int batch, float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
@@ -215,15 +222,17 @@ whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const in
   int tile = blockIdx.x;
   if (tile < ntiles) stage_tile(tile, warp, W_WARPS);
 
-  for (; tile < ntiles; tile += gridDim.x) {
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
     const int clip = tile / W_TILES_PER_CLIP;
     const int f0 = (tile - clip * W_TILES_PER_CLIP) * W_TILE;
 
     cp_async_commit_wait_all();
     __syncthreads();                       // audio(tile) visible; E is free (previous mel finished)
+    W_MARK(0);
 
     // ---- pass 1: 16 tasks, one per warp ---------------------------------------------------------
     w_pass1(warp, s_audio + lane * W_PITCH, s_e + lane, s_off, s_win);
+    W_MARK(1);
     __syncthreads();                       // E complete; the audio tile is dead from here on
 
     // ---- pass 2: 13 tasks on warps 0..12; warps 13..15 prefetch the next tile's audio meanwhile ----
@@ -233,6 +242,7 @@ whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const in
       const int next = tile + gridDim.x;
       if (next < ntiles) stage_tile(next, warp - W_P2_TASKS, W_WARPS - W_P2_TASKS);
     }
+    W_MARK(2);
     __syncthreads();
 
     // ---- mel + log + per-clip max ----------------------------------------------------------------
@@ -265,6 +275,7 @@ whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const in
       // positive floats order like their bit patterns; the slot is zeroed before the launch
       if (lane == 0 && emax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(emax));
     }
+    W_MARK(3);
   }
 }
 
@@ -594,6 +605,13 @@ int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples
   if (e != cudaSuccess) return fail_cuda(e, "urban_mel_kernel launch");
   return B200MEL_OK;
 }
+
+#ifdef W_TRACE
+int b200mel_debug_set_trace(void* dev_ptr) {
+  long long* p = (long long*)dev_ptr;
+  return cudaMemcpyToSymbol(g_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 int64_t b200mel_get_table(int preset, int table, float* dst, int64_t capacity) {
   if (!dst) return fail(B200MEL_ERR_BAD_ARG, "get_table: dst is NULL");
