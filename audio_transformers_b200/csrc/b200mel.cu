@@ -53,7 +53,10 @@ constexpr int W_SM_AUDIO = ((W_ROWS * W_PITCH + 31) / 32) * 32;  // floats
 constexpr int W_EROWS = 16 * 26;                                 // 16 classes x 13 complex outputs
 constexpr int W_SM_E = W_EROWS * 32 * 2;                         // floats (float2 per lane and row)
 constexpr int W_SM_TAB = 2 * 16 * 28;                            // pass-1 offsets (int) + window taps (float)
-constexpr int W_SMEM_BYTES = (W_SM_E + W_SM_AUDIO + W_SM_TAB) * 4;
+constexpr int W_PROWS = 13 * 16;                                 // power rows: k2 * 16 + k1
+constexpr int W_SM_P = W_PROWS * 32 * 2;                         // floats (float2 per lane and row)
+constexpr int W_SMEM_BYTES = (W_SM_E + W_SM_P + W_SM_AUDIO + W_SM_TAB) * 4;
+static_assert(W_SMEM_BYTES <= 227 * 1024, "Whisper tile does not fit in shared memory");
 constexpr int W_LANE2 = 32 * W_PITCH;                            // float offset of a lane's second frame (f0 + 32 + lane)
 
 // y = (log10(e) + 4) / 4 = log2(e) * (log10(2)/4) + 1; e >= 1e-10 so the ftz approx form is exact enough
@@ -77,10 +80,15 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // rules out 16-byte destinations); tiles touching a clip edge take the generic path that applies the
 // reflect padding of the 480000-sample padded clip and the zero fill past the clip length.
 // `part`/`nparts`: the rows are split over the warps that take part in the copy.
+// (A register path -- LDG.32 before pass 2, STS.32 after it -- was tried and is slower: with 206 KB of
+// the SM carved out as shared memory the few L1 lines left throttle the loads in flight.)
 __device__ __forceinline__ void w_stage(const float* __restrict__ src, int L, int f0, float* __restrict__ s_audio,
                                         int part, int nparts, int lane) {
   const int g0 = f0 * W_HOP - W_NFFT / 2;
   const bool interior = (g0 >= 0) && (g0 + W_ROWS * W_HOP <= L);
+#ifdef W_EXP_NOSTAGE
+  if (interior) return;
+#endif
   if (interior) {
     const float* g = src + g0 + part * W_HOP + lane;
     float* d = s_audio + part * W_PITCH + lane;
@@ -140,9 +148,10 @@ __device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_l
 }
 
 // ---- pass 2: complex 16-point DFT for k2 (warp-uniform, runtime); |X|^2 written back in place ----
-__device__ __forceinline__ void w_pass2(int k2, float2* __restrict__ e_lane) {
+__device__ __forceinline__ void w_pass2(int k2, const float2* __restrict__ e_lane, float2* __restrict__ p_lane) {
   float2 yr[16], yi[16], Xr[16], Xi[16];
-  float2* base = e_lane + k2 * 64;      // rows a*26 + 2*k2 (re) and a*26 + 2*k2 + 1 (im)
+  const float2* base = e_lane + k2 * 64;      // rows a*26 + 2*k2 (re) and a*26 + 2*k2 + 1 (im)
+  float2* dst = p_lane + k2 * (16 * 32);      // power rows k2*16 + k1
 #pragma unroll
   for (int a = 0; a < 16; ++a) {
     yr[a] = base[a * (26 * 32)];
@@ -150,13 +159,14 @@ __device__ __forceinline__ void w_pass2(int k2, float2* __restrict__ e_lane) {
   }
   b2::cplx_dft16(yr, yi, Xr, Xi);
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) base[k1 * (26 * 32)] = b2::vfma(Xr[k1], Xr[k1], b2::vmul(Xi[k1], Xi[k1]));
+  for (int k1 = 0; k1 < 16; ++k1) dst[k1 * 32] = b2::vfma(Xr[k1], Xr[k1], b2::vmul(Xi[k1], Xi[k1]));
 }
 
 // ---- mel: filters are specialised at compile time per warp (row offsets and weights are immediates) ----
 B2_CX int w_mel_len(int m) { const int t[80] = kWMelLen_INIT; return t[m]; }
 B2_CX int w_mel_off(int m) { const int t[80] = kWMelOff_INIT; return t[m]; }
-B2_CX int w_mel_row(int i) { const int t[B200MEL_W_NNZ] = kWMelRow_INIT; return t[i]; }
+// the generated table names the tap's bin by (k1, k2) as k1*26 + 2*k2; the power buffer row is k2*16 + k1
+B2_CX int w_mel_row(int i) { const int t[B200MEL_W_NNZ] = kWMelRow_INIT; return ((t[i] % 26) / 2) * 16 + t[i] / 26; }
 B2_CX float w_mel_wt(int i) { const float t[B200MEL_W_NNZ] = kWMelW_INIT; return t[i]; }
 
 template <int I, int END>
@@ -190,6 +200,38 @@ __device__ __forceinline__ void w_mel_warp(const float2* __restrict__ p_lane, fl
   w_mel_one<W + 64>(p_lane, out_col, valid0, valid1, emax);
 }
 
+// ---- mel + log + per-clip max for one tile whose power spectrum sits in P ------------------------
+__device__ __forceinline__ void w_mel_phase(int warp, int lane, int clip, int f0, const float2* __restrict__ s_p,
+                                            float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
+  const int frame0 = f0 + lane, frame1 = f0 + 32 + lane;
+  const bool valid0 = frame0 < W_NFRAME, valid1 = frame1 < W_NFRAME;
+  const float2* pl = s_p + lane;
+  float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame0;
+  float emax = 0.0f;
+  switch (warp) {
+    case 0: w_mel_warp<0>(pl, out_col, valid0, valid1, emax); break;
+    case 1: w_mel_warp<1>(pl, out_col, valid0, valid1, emax); break;
+    case 2: w_mel_warp<2>(pl, out_col, valid0, valid1, emax); break;
+    case 3: w_mel_warp<3>(pl, out_col, valid0, valid1, emax); break;
+    case 4: w_mel_warp<4>(pl, out_col, valid0, valid1, emax); break;
+    case 5: w_mel_warp<5>(pl, out_col, valid0, valid1, emax); break;
+    case 6: w_mel_warp<6>(pl, out_col, valid0, valid1, emax); break;
+    case 7: w_mel_warp<7>(pl, out_col, valid0, valid1, emax); break;
+    case 8: w_mel_warp<8>(pl, out_col, valid0, valid1, emax); break;
+    case 9: w_mel_warp<9>(pl, out_col, valid0, valid1, emax); break;
+    case 10: w_mel_warp<10>(pl, out_col, valid0, valid1, emax); break;
+    case 11: w_mel_warp<11>(pl, out_col, valid0, valid1, emax); break;
+    case 12: w_mel_warp<12>(pl, out_col, valid0, valid1, emax); break;
+    case 13: w_mel_warp<13>(pl, out_col, valid0, valid1, emax); break;
+    case 14: w_mel_warp<14>(pl, out_col, valid0, valid1, emax); break;
+    default: w_mel_warp<15>(pl, out_col, valid0, valid1, emax); break;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  // positive floats order like their bit patterns; the slot is zeroed before the launch
+  if (lane == 0 && emax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(emax));
+}
+
 #ifdef W_TRACE
 __device__ long long* g_trace = nullptr;     // [iter][4 marks][16 warps] clock64 of CTA 0 (debug builds only)
 #define W_MARK(k) do { if (blockIdx.x == 0 && lane == 0 && it < 32 && g_trace) g_trace[(it * 4 + (k)) * 16 + warp] = clock64(); } while (0)
@@ -197,14 +239,23 @@ __device__ long long* g_trace = nullptr;     // [iter][4 marks][16 warps] clock6
 #define W_MARK(k) do { } while (0)
 #endif
 
+#ifndef W_MEL_FIRST_MASK
+#define W_MEL_FIRST_MASK 0x0f0f            // warps (bit set) that run their mel share before their pass-1 task
+#endif
+
+// Persistent CTA, one per SM, looping over (clip, 64-frame tile).  Two block barriers per tile:
+//   phase A   mel(previous tile, from P)  +  pass 1(this tile, audio -> E)     [LSU-heavy + FMA-heavy work
+//             run side by side: half of the warps do their mel share first, the other half their DFT task]
+//   phase B   cp.async prefetch of the next tile's audio (all warps)  +  pass 2(this tile, E -> P) on warps 0..12
 __global__ void __launch_bounds__(W_THREADS, 1)
 whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
                       int batch, float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
   extern __shared__ __align__(16) float smem[];
   float2* s_e = reinterpret_cast<float2*>(smem);
-  float* s_audio = smem + W_SM_E;
-  int* s_off = reinterpret_cast<int*>(smem + W_SM_E + W_SM_AUDIO);
-  float* s_win = smem + W_SM_E + W_SM_AUDIO + 16 * 28;
+  float2* s_p = reinterpret_cast<float2*>(smem + W_SM_E);
+  float* s_audio = smem + W_SM_E + W_SM_P;
+  int* s_off = reinterpret_cast<int*>(smem + W_SM_E + W_SM_P + W_SM_AUDIO);
+  float* s_win = smem + W_SM_E + W_SM_P + W_SM_AUDIO + 16 * 28;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntiles = batch * W_TILES_PER_CLIP;
@@ -218,64 +269,48 @@ whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const in
     const int c = t / W_TILES_PER_CLIP;
     w_stage(wave + (size_t)c * (size_t)stride, clip_len(c), (t - c * W_TILES_PER_CLIP) * W_TILE, s_audio, part, nparts, lane);
   };
+  const bool mel_first = (W_MEL_FIRST_MASK >> warp) & 1;
 
   int tile = blockIdx.x;
   if (tile < ntiles) stage_tile(tile, warp, W_WARPS);
+  int prev_clip = -1, prev_f0 = 0;
 
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-    const int clip = tile / W_TILES_PER_CLIP;
-    const int f0 = (tile - clip * W_TILES_PER_CLIP) * W_TILE;
-
+  for (int it = 0;; tile += gridDim.x, ++it) {
+    const bool have = tile < ntiles;
     cp_async_commit_wait_all();
-    __syncthreads();                       // audio(tile) visible; E is free (previous mel finished)
+    __syncthreads();                       // audio(tile) visible; P(previous tile) complete; E is free
     W_MARK(0);
 
-    // ---- pass 1: 16 tasks, one per warp ---------------------------------------------------------
-    w_pass1(warp, s_audio + lane * W_PITCH, s_e + lane, s_off, s_win);
-    W_MARK(1);
-    __syncthreads();                       // E complete; the audio tile is dead from here on
-
-    // ---- pass 2: 13 tasks on warps 0..12; warps 13..15 prefetch the next tile's audio meanwhile ----
-    if (warp < W_P2_TASKS) {
-      w_pass2(warp, s_e + lane);
-    } else {
-      const int next = tile + gridDim.x;
-      if (next < ntiles) stage_tile(next, warp - W_P2_TASKS, W_WARPS - W_P2_TASKS);
-    }
-    W_MARK(2);
-    __syncthreads();
-
-    // ---- mel + log + per-clip max ----------------------------------------------------------------
-    {
-      const int frame0 = f0 + lane, frame1 = f0 + 32 + lane;
-      const bool valid0 = frame0 < W_NFRAME, valid1 = frame1 < W_NFRAME;
-      const float2* pl = s_e + lane;
-      float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame0;
-      float emax = 0.0f;
-      switch (warp) {
-        case 0: w_mel_warp<0>(pl, out_col, valid0, valid1, emax); break;
-        case 1: w_mel_warp<1>(pl, out_col, valid0, valid1, emax); break;
-        case 2: w_mel_warp<2>(pl, out_col, valid0, valid1, emax); break;
-        case 3: w_mel_warp<3>(pl, out_col, valid0, valid1, emax); break;
-        case 4: w_mel_warp<4>(pl, out_col, valid0, valid1, emax); break;
-        case 5: w_mel_warp<5>(pl, out_col, valid0, valid1, emax); break;
-        case 6: w_mel_warp<6>(pl, out_col, valid0, valid1, emax); break;
-        case 7: w_mel_warp<7>(pl, out_col, valid0, valid1, emax); break;
-        case 8: w_mel_warp<8>(pl, out_col, valid0, valid1, emax); break;
-        case 9: w_mel_warp<9>(pl, out_col, valid0, valid1, emax); break;
-        case 10: w_mel_warp<10>(pl, out_col, valid0, valid1, emax); break;
-        case 11: w_mel_warp<11>(pl, out_col, valid0, valid1, emax); break;
-        case 12: w_mel_warp<12>(pl, out_col, valid0, valid1, emax); break;
-        case 13: w_mel_warp<13>(pl, out_col, valid0, valid1, emax); break;
-        case 14: w_mel_warp<14>(pl, out_col, valid0, valid1, emax); break;
-        default: w_mel_warp<15>(pl, out_col, valid0, valid1, emax); break;
+    // ---- phase A ------------------------------------------------------------------------------------
+#pragma unroll 1
+    for (int step = 0; step < 2; ++step) {
+      if ((step == 0) == mel_first) {
+        if (prev_clip >= 0) w_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, clip_max_bits);
+      } else if (have) {
+#ifdef W_EXP_STAGGER_A
+        { const long long t_start = clock64(); const int wait = ((warp >> 2) & 1) * W_EXP_STAGGER_A;
+          while (clock64() - t_start < wait) { } }
+#endif
+        w_pass1(warp, s_audio + lane * W_PITCH, s_e + lane, s_off, s_win);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
-      // positive floats order like their bit patterns; the slot is zeroed before the launch
-      if (lane == 0 && emax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(emax));
     }
-    W_MARK(3);
+    W_MARK(1);
+    if (!have) break;
+    __syncthreads();                       // E complete; the audio tile and P are dead from here on
+
+    // ---- phase B ------------------------------------------------------------------------------------
+#ifdef W_EXP_STAGGER_B
+    { const long long t_start = clock64(); const int wait = (warp >> 2) * W_EXP_STAGGER_B;
+      while (clock64() - t_start < wait) { } }
+#endif
+    {   // every warp first queues its share of the next tile's audio (cp.async, lands during pass 2)
+      const int next = tile + gridDim.x;
+      if (next < ntiles) stage_tile(next, warp, W_WARPS);
+    }
+    if (warp < W_P2_TASKS) w_pass2(warp, s_e + lane, s_p + lane);
+    W_MARK(2);
+    prev_clip = tile / W_TILES_PER_CLIP;
+    prev_f0 = (tile - prev_clip * W_TILES_PER_CLIP) * W_TILE;
   }
 }
 
