@@ -18,9 +18,11 @@
 //   A second, tiny in-place pass applies max(y, ymax - 2) once the clip maximum is known.
 //
 // Nothing but the audio (read once per tile, +7 % halo) and the features touches HBM.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/b200mel.h"
@@ -46,18 +48,25 @@ constexpr int W_TILES_PER_CLIP = (W_NFRAME + W_TILE - 1) / W_TILE;   // 47
 constexpr int W_THREADS = 512;
 constexpr int W_WARPS = W_THREADS / 32;                          // 16 = number of pass-1 tasks
 constexpr int W_P2_TASKS = 13;                                   // warps 0..12 run pass 2, warps 13..15 prefetch audio
-constexpr int W_SPAN = (W_TILE - 1) * W_HOP + W_NFFT;            // 10480 samples staged per tile
-constexpr int W_PITCH = W_HOP + 1;                               // 161: odd pitch -> conflict-free lanes
-constexpr int W_ROWS = (W_SPAN + W_HOP - 1) / W_HOP;             // 66 rows (last one half full)
+constexpr int W_ROWS = ((W_TILE - 1) * W_HOP + W_NFFT + W_HOP - 1) / W_HOP;   // 66 rows of 160 samples span one tile
+// Audio tile layout: row r holds samples [160 r, 160 r + 164) of the tile at a pitch of 164 words, written by
+// ONE TMA box per tile (TMA is 16-byte granular on both sides, so an odd pitch is not available; cp.async
+// at 4-byte granularity costs ~8 LSU cycles per warp instruction and was 30 % of the kernel).  With 16-byte
+// aligned rows, 32 lanes reading the same sample of 32 different rows would hit only 8 banks, so pass 1
+// gives a warp 8 frame pairs x 4 CONSECUTIVE tasks instead: task a -> a+1 moves the sample index by 25
+// (= 1 mod 4), which spreads the four 8-lane groups over the four bank residues: conflict free.
+constexpr int W_PITCH = W_HOP + 4;                               // 164
 constexpr int W_SM_AUDIO = ((W_ROWS * W_PITCH + 31) / 32) * 32;  // floats
-constexpr int W_EROWS = 16 * 26;                                 // 16 classes x 13 complex outputs
-constexpr int W_SM_E = W_EROWS * 32 * 2;                         // floats (float2 per lane and row)
+constexpr int W_TX_BYTES = W_ROWS * W_PITCH * 4;                 // bytes one TMA box delivers
+constexpr int W_TMAP_X = 284;                                    // tensor-map extent of the sample axis (see the host code)
+constexpr int W_EBLK = 26 * 32 + 8;                              // float2 per task block: 26 rows + 8 pad (pass-1 stores of two tasks in one half-warp land in different banks)
+constexpr int W_SM_E = 16 * W_EBLK * 2;                          // floats
 constexpr int W_SM_TAB = 2 * 16 * 28;                            // pass-1 offsets (int) + window taps (float)
 constexpr int W_PROWS = 13 * 16;                                 // power rows: k2 * 16 + k1
 constexpr int W_SM_P = W_PROWS * 32 * 2;                         // floats (float2 per lane and row)
-constexpr int W_SMEM_BYTES = (W_SM_E + W_SM_P + W_SM_AUDIO + W_SM_TAB) * 4;
+constexpr int W_SMEM_BYTES = (W_SM_AUDIO + W_SM_E + W_SM_P + W_SM_TAB) * 4 + 16;   // + the TMA mbarrier
 static_assert(W_SMEM_BYTES <= 227 * 1024, "Whisper tile does not fit in shared memory");
-constexpr int W_LANE2 = 32 * W_PITCH;                            // float offset of a lane's second frame (f0 + 32 + lane)
+constexpr int W_LANE2 = 8 * W_PITCH;                             // float offset of a lane's second frame (8 frames on)
 
 // y = (log10(e) + 4) / 4 = log2(e) * (log10(2)/4) + 1; e >= 1e-10 so the ftz approx form is exact enough
 __device__ __forceinline__ float w_norm_log(float e) {
@@ -74,50 +83,88 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// ---- mbarrier / TMA primitives -----------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra W_DONE_%=;\n"
+      "bra W_WAIT_%=;\n"
+      "W_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(float* smem_dst, const CUtensorMap* tmap, int x, int y, int z,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- stage one tile of audio into shared memory ------------------------------------------------
-// Row r of the tile holds samples [160 r, 160 r + 160) at pitch 161.  Interior tiles stream with
-// cp.async (4-byte granularity: the odd pitch is what makes the 32 frame-lanes conflict free, and it
-// rules out 16-byte destinations); tiles touching a clip edge take the generic path that applies the
-// reflect padding of the 480000-sample padded clip and the zero fill past the clip length.
-// `part`/`nparts`: the rows are split over the warps that take part in the copy.
-// (A register path -- LDG.32 before pass 2, STS.32 after it -- was tried and is slower: with 206 KB of
-// the SM carved out as shared memory the few L1 lines left throttle the loads in flight.)
-__device__ __forceinline__ void w_stage(const float* __restrict__ src, int L, int f0, float* __restrict__ s_audio,
-                                        int part, int nparts, int lane) {
-  const int g0 = f0 * W_HOP - W_NFFT / 2;
-  const bool interior = (g0 >= 0) && (g0 + W_ROWS * W_HOP <= L);
-#ifdef W_EXP_NOSTAGE
-  if (interior) return;
-#endif
-  if (interior) {
-    const float* g = src + g0 + part * W_HOP + lane;
-    float* d = s_audio + part * W_PITCH + lane;
-#pragma unroll 2
-    for (int r = part; r < W_ROWS; r += nparts) {
+struct WTile {
+  const float* src;     // clip base
+  int clip, f0;
+  int L;                // valid samples (<= 480000)
+  bool tma;             // interior tile: fetched by TMA; otherwise the generic path below
+};
+
+__device__ __forceinline__ WTile w_tile(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
+                                        int tile, int use_tma) {
+  WTile t;
+  t.clip = tile / W_TILES_PER_CLIP;
+  t.f0 = (tile - t.clip * W_TILES_PER_CLIP) * W_TILE;
+  const long long len_ll = lengths ? (long long)__ldg(lengths + t.clip) : stride;
+  t.L = (int)(len_ll < 0 ? 0 : (len_ll > W_NSAMP ? W_NSAMP : len_ll));
+  t.src = wave + (size_t)t.clip * (size_t)stride;
+  const long long g0 = (long long)t.f0 * W_HOP - W_NFFT / 2;
+  // every sample of the tile is real audio (no reflection, no zero fill), and the 4 words of row slack the
+  // boxes also fetch stay inside the clip's row of the buffer
+  t.tma = use_tma && g0 >= 0 && g0 + W_ROWS * W_HOP <= t.L && g0 + W_ROWS * W_HOP + 4 <= stride;
+  return t;
+}
+
+// Interior tiles: one TMA box of 66 rows x 164 samples.  The tensor map views the audio as
+// [clip][hop index y][x < 284] with a y-stride of 160 samples (overlapping rows), so row r of the tile is
+// (x = 120, y = f0 - 2 + r).  Issued by one thread.
+__device__ __forceinline__ void w_stage_tma(const WTile& t, const CUtensorMap* tmap, float* s_audio, unsigned long long* bar) {
+  fence_proxy_async();               // earlier generic-proxy accesses to the tile vs. the async-proxy writes
+  mbar_arrive_expect_tx(bar, W_TX_BYTES);
+  tma_load_3d(s_audio, tmap, 120, t.f0 - 2, t.clip, bar);
+}
+
+// Tiles touching a clip edge: the same layout written with ordinary stores, applying the reflect padding of
+// the 480000-sample padded clip and the zero fill past the clip length.  `part`/`nparts` split the rows.
+__device__ __forceinline__ void w_stage_generic(const WTile& t, float* __restrict__ s_audio, int part, int nparts, int lane) {
+  const int g0 = t.f0 * W_HOP - W_NFFT / 2;
+  for (int r = part; r < W_ROWS; r += nparts) {
+    float* d = s_audio + r * W_PITCH + lane;
+    const int gs = g0 + r * W_HOP + lane;
 #pragma unroll
-      for (int k = 0; k < W_HOP / 32; ++k) cp_async4(d + 32 * k, g + 32 * k);
-      g += nparts * W_HOP;
-      d += nparts * W_PITCH;
-    }
-  } else {
-    for (int r = part; r < W_ROWS; r += nparts) {
-#pragma unroll
-      for (int k = 0; k < W_HOP / 32; ++k) {
-        const int g = g0 + r * W_HOP + lane + 32 * k;
-        const int j = g < 0 ? -g : (g >= W_NSAMP ? 2 * (W_NSAMP - 1) - g : g);
-        s_audio[r * W_PITCH + lane + 32 * k] = (j >= 0 && j < L) ? __ldg(src + j) : 0.0f;
-      }
+    for (int k = 0; k < W_HOP / 32; ++k) {
+      const int g = gs + 32 * k;
+      const int j = g < 0 ? -g : (g >= W_NSAMP ? 2 * (W_NSAMP - 1) - g : g);
+      d[32 * k] = (j >= 0 && j < t.L) ? __ldg(t.src + j) : 0.0f;
     }
   }
 }
 
-// ---- pass 1: windowed real 25-point DFT of residue class a (warp-uniform) ----------------------
-// Good-Thomas input order and window taps come from tables (one code body for all 16 classes: a fully
-// specialised variant was instruction-cache bound, profiles/r01_v1).  The tables are read from a
-// shared-memory copy with broadcast 128-bit loads: register-indexed constant loads (LDC) of the same
-// data were the top stall of the previous version (profiles/r01_v4).  Each lane carries two frames
-// (f0 + lane, f0 + 32 + lane) as a packed float2.
-__device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_lane, float2* __restrict__ e_lane,
+// ---- pass 1: windowed real 25-point DFT of residue class a --------------------------------------
+// A warp works on 8 frame pairs x 4 consecutive classes: lane = (g, i), class a = 4 q + g, frames
+// 16 fg + i and 16 fg + 8 + i packed as a float2 (q = warp & 3, fg = warp >> 2).  Good-Thomas input order
+// and window taps come from shared-memory tables, one row per class (one code body for all 16 classes: a
+// fully specialised variant was instruction-cache bound, profiles/r01_v1); the 8 lanes of a group read the
+// same 16 bytes, so a table load is 4 wavefronts.
+__device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_lane, float2* __restrict__ e_dst,
                                         const int* __restrict__ s_off, const float* __restrict__ s_win) {
   float2 x[25], o[25];
   int off[28];
@@ -140,11 +187,10 @@ __device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_l
     w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
   }
   b2::real_dft25(x, w, o);
-  float2* dst = e_lane + a * (26 * 32);
-  dst[0] = o[0];
-  dst[32] = make_float2(0.0f, 0.0f);    // Im X0 = 0 keeps pass 2 free of special cases
+  e_dst[0] = o[0];
+  e_dst[32] = make_float2(0.0f, 0.0f);    // Im X0 = 0 keeps pass 2 free of special cases
 #pragma unroll
-  for (int c = 1; c < 25; ++c) dst[(c + 1) * 32] = o[c];
+  for (int c = 1; c < 25; ++c) e_dst[(c + 1) * 32] = o[c];
 }
 
 // ---- pass 2: complex 16-point DFT for k2 (warp-uniform, runtime); |X|^2 written back in place ----
@@ -154,8 +200,8 @@ __device__ __forceinline__ void w_pass2(int k2, const float2* __restrict__ e_lan
   float2* dst = p_lane + k2 * (16 * 32);      // power rows k2*16 + k1
 #pragma unroll
   for (int a = 0; a < 16; ++a) {
-    yr[a] = base[a * (26 * 32)];
-    yi[a] = base[a * (26 * 32) + 32];
+    yr[a] = base[a * W_EBLK];
+    yi[a] = base[a * W_EBLK + 32];
   }
   b2::cplx_dft16(yr, yi, Xr, Xi);
 #pragma unroll
@@ -187,7 +233,7 @@ __device__ __forceinline__ void w_mel_one(const float2* __restrict__ p_lane, flo
   w_mel_taps<OFF, OFF + LEN>(p_lane, acc);
   const float e0 = fmaxf(acc.x, 1e-10f), e1 = fmaxf(acc.y, 1e-10f);
   if (valid0) { emax = fmaxf(emax, e0); out_col[(size_t)M * W_NFRAME] = w_norm_log(e0); }
-  if (valid1) { emax = fmaxf(emax, e1); out_col[(size_t)M * W_NFRAME + 32] = w_norm_log(e1); }
+  if (valid1) { emax = fmaxf(emax, e1); out_col[(size_t)M * W_NFRAME + 8] = w_norm_log(e1); }
 }
 
 template <int W>
@@ -203,7 +249,8 @@ __device__ __forceinline__ void w_mel_warp(const float2* __restrict__ p_lane, fl
 // ---- mel + log + per-clip max for one tile whose power spectrum sits in P ------------------------
 __device__ __forceinline__ void w_mel_phase(int warp, int lane, int clip, int f0, const float2* __restrict__ s_p,
                                             float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
-  const int frame0 = f0 + lane, frame1 = f0 + 32 + lane;
+  // column `lane` of E / P carries frames 16 (lane / 8) + lane % 8 and that + 8 (see w_pass1)
+  const int frame0 = f0 + 16 * (lane >> 3) + (lane & 7), frame1 = frame0 + 8;
   const bool valid0 = frame0 < W_NFRAME, valid1 = frame1 < W_NFRAME;
   const float2* pl = s_p + lane;
   float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame0;
@@ -246,38 +293,48 @@ __device__ long long* g_trace = nullptr;     // [iter][4 marks][16 warps] clock6
 // Persistent CTA, one per SM, looping over (clip, 64-frame tile).  Two block barriers per tile:
 //   phase A   mel(previous tile, from P)  +  pass 1(this tile, audio -> E)     [LSU-heavy + FMA-heavy work
 //             run side by side: half of the warps do their mel share first, the other half their DFT task]
-//   phase B   cp.async prefetch of the next tile's audio (all warps)  +  pass 2(this tile, E -> P) on warps 0..12
+//   phase B   TMA prefetch of the next tile's audio (one box, issued by one thread, lands on an mbarrier)
+//             +  pass 2(this tile, E -> P) on warps 0..12
 __global__ void __launch_bounds__(W_THREADS, 1)
-whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
+whisper_logmel_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma,
+                      const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
                       int batch, float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
-  extern __shared__ __align__(16) float smem[];
-  float2* s_e = reinterpret_cast<float2*>(smem);
-  float2* s_p = reinterpret_cast<float2*>(smem + W_SM_E);
-  float* s_audio = smem + W_SM_E + W_SM_P;
-  int* s_off = reinterpret_cast<int*>(smem + W_SM_E + W_SM_P + W_SM_AUDIO);
-  float* s_win = smem + W_SM_E + W_SM_P + W_SM_AUDIO + 16 * 28;
+  extern __shared__ __align__(1024) float smem[];
+  float* s_audio = smem;
+  float2* s_e = reinterpret_cast<float2*>(smem + W_SM_AUDIO);
+  float2* s_p = reinterpret_cast<float2*>(smem + W_SM_AUDIO + W_SM_E);
+  int* s_off = reinterpret_cast<int*>(smem + W_SM_AUDIO + W_SM_E + W_SM_P);
+  float* s_win = smem + W_SM_AUDIO + W_SM_E + W_SM_P + 16 * 28;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + W_SM_AUDIO + W_SM_E + W_SM_P + W_SM_TAB);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntiles = batch * W_TILES_PER_CLIP;
   if (tid < 16 * 28) { s_off[tid] = c_wp1_off[tid]; s_win[tid] = c_wp1_win[tid]; }
+  if (tid == 0) { mbar_init(s_bar, 1); fence_proxy_async(); }
+  __syncthreads();
 
-  auto clip_len = [&](int clip) {
-    long long len_ll = lengths ? (long long)__ldg(lengths + clip) : stride;
-    return (int)(len_ll < 0 ? 0 : (len_ll > W_NSAMP ? W_NSAMP : len_ll));
-  };
-  auto stage_tile = [&](int t, int part, int nparts) {
-    const int c = t / W_TILES_PER_CLIP;
-    w_stage(wave + (size_t)c * (size_t)stride, clip_len(c), (t - c * W_TILES_PER_CLIP) * W_TILE, s_audio, part, nparts, lane);
-  };
+  // pass-1 role of this lane: class a, frame pair (16 fg + i, 16 fg + 8 + i) = column 8 fg + i of E
+  const int p1_a = 4 * (warp & 3) + (lane >> 3);
+  const int p1_col = 8 * (warp >> 2) + (lane & 7);
+  const float* audio_lane = s_audio + (16 * (warp >> 2) + (lane & 7)) * W_PITCH;
+  float2* p1_dst = s_e + p1_a * W_EBLK + p1_col;
   const bool mel_first = (W_MEL_FIRST_MASK >> warp) & 1;
+  constexpr int STAGE_WARP = W_P2_TASKS;     // first warp without a pass-2 task
 
   int tile = blockIdx.x;
-  if (tile < ntiles) stage_tile(tile, warp, W_WARPS);
+  unsigned tma_parity = 0;
+  bool cur_tma = false;
+  if (tile < ntiles) {
+    const WTile t = w_tile(wave, stride, lengths, tile, use_tma);
+    cur_tma = t.tma;
+    if (t.tma) { if (tid == STAGE_WARP * 32) w_stage_tma(t, &tmap, s_audio, s_bar); }
+    else w_stage_generic(t, s_audio, warp, W_WARPS, lane);
+  }
   int prev_clip = -1, prev_f0 = 0;
 
   for (int it = 0;; tile += gridDim.x, ++it) {
     const bool have = tile < ntiles;
-    cp_async_commit_wait_all();
+    if (have && cur_tma) { mbar_wait(s_bar, tma_parity); tma_parity ^= 1u; }
     __syncthreads();                       // audio(tile) visible; P(previous tile) complete; E is free
     W_MARK(0);
 
@@ -287,11 +344,7 @@ whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const in
       if ((step == 0) == mel_first) {
         if (prev_clip >= 0) w_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, clip_max_bits);
       } else if (have) {
-#ifdef W_EXP_STAGGER_A
-        { const long long t_start = clock64(); const int wait = ((warp >> 2) & 1) * W_EXP_STAGGER_A;
-          while (clock64() - t_start < wait) { } }
-#endif
-        w_pass1(warp, s_audio + lane * W_PITCH, s_e + lane, s_off, s_win);
+        w_pass1(p1_a, audio_lane, p1_dst, s_off, s_win);
       }
     }
     W_MARK(1);
@@ -303,9 +356,15 @@ whisper_logmel_kernel(const float* __restrict__ wave, long long stride, const in
     { const long long t_start = clock64(); const int wait = (warp >> 2) * W_EXP_STAGGER_B;
       while (clock64() - t_start < wait) { } }
 #endif
-    {   // every warp first queues its share of the next tile's audio (cp.async, lands during pass 2)
+    {
       const int next = tile + gridDim.x;
-      if (next < ntiles) stage_tile(next, warp, W_WARPS);
+      cur_tma = false;
+      if (next < ntiles) {
+        const WTile t = w_tile(wave, stride, lengths, next, use_tma);
+        cur_tma = t.tma;
+        if (t.tma) { if (tid == STAGE_WARP * 32) w_stage_tma(t, &tmap, s_audio, s_bar); }
+        else w_stage_generic(t, s_audio, warp, W_WARPS, lane);
+      }
     }
     if (warp < W_P2_TASKS) w_pass2(warp, s_e + lane, s_p + lane);
     W_MARK(2);
@@ -405,7 +464,7 @@ __device__ __forceinline__ void u_pass2(int k2, const float* __restrict__ e_lane
 __global__ void __launch_bounds__(U_THREADS, 1)
 urban_mel_kernel(const float* __restrict__ wave, long long stride, int n_samples, int n_frames, int tiles_per_clip,
                  int batch, float log_eps, float* __restrict__ out) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(1024) float smem[];
   float* s_e = smem;
   float* s_audio = smem + U_SM_E;                     // later reused as P[513][32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -479,10 +538,16 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 }  // namespace
 
+// cuTensorMapEncodeTiled, resolved through the runtime so that the library does not link libcuda directly
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 struct b200mel_handle {
   int device;
   int preset;
   int sm_count;
+  tmap_encode_fn encode = nullptr;   // Whisper preset: TMA descriptor encoder
   // optional benchmark instrumentation (b200mel_profile_begin/end)
   bool prof_on = false;
   int prof_cap = 0, prof_n = 0;
@@ -521,6 +586,16 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
   cudaSetDevice(prev);
   if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute");
   b200mel_handle* h = new b200mel_handle(device, preset, prop.multiProcessorCount);
+  if (preset == B200MEL_PRESET_WHISPER) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      delete h;
+      return fail(B200MEL_ERR_CUDA, "b200mel_create: cuTensorMapEncodeTiled is not available from this driver");
+    }
+    h->encode = (tmap_encode_fn)fn;
+  }
   *out = h;
   return B200MEL_OK;
 }
@@ -589,12 +664,29 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   unsigned int* clip_max = (unsigned int*)workspace;
   cudaError_t e = cudaMemsetAsync(clip_max, 0, (size_t)batch * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
+  // TMA view of the audio: [clip][y][x], element (x, y, clip) = wave[clip * stride + 160 y + x], x < 284.  Rows
+  // overlap (y-stride 160 samples < 284), which is what lets a box start at any sample with 16-byte aligned
+  // strides.  NY is chosen so that every in-bounds element lies inside its clip's row of the buffer.
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  int use_tma = 0;
+  if (stride_samples >= W_TMAP_X) {
+    const cuuint64_t dims[3] = {(cuuint64_t)W_TMAP_X, (cuuint64_t)((stride_samples - W_TMAP_X) / W_HOP + 1), (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)W_HOP * sizeof(float), (cuuint64_t)stride_samples * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)W_PITCH, (cuuint32_t)W_ROWS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = h->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)wave, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200MEL_ERR_CUDA, "whisper_logmel: cuTensorMapEncodeTiled failed");
+    use_tma = getenv("B200MEL_DEBUG_NO_TMA") ? 0 : 1;   // debug knob: every tile through the generic staging path
+  }
   const int ntiles = batch * W_TILES_PER_CLIP;
   const int grid_main = ntiles < h->sm_count ? ntiles : h->sm_count;   // persistent: one 512-thread CTA per SM
   const bool prof = h->prof_on && h->prof_n < h->prof_cap;
   if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
   whisper_logmel_kernel<<<grid_main, W_THREADS, W_SMEM_BYTES, stream>>>(
-      wave, (long long)stride_samples, lengths, batch, out, clip_max);
+      tmap, use_tma, wave, (long long)stride_samples, lengths, batch, out, clip_max);
   if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "whisper_logmel_kernel launch");
