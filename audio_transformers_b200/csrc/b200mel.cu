@@ -209,41 +209,68 @@ __device__ __forceinline__ void w_pass2(int k2, const float2* __restrict__ e_lan
 }
 
 // ---- mel: filters are specialised at compile time per warp (row offsets and weights are immediates) ----
+// Each warp owns a CONTIGUOUS run of filters, balanced by cost (taps + a fixed per-filter epilogue).  Neighbouring
+// triangles overlap by half, so the warp first loads the union of its bins once (about half the loads of a
+// filter-by-filter walk) and then runs the independent accumulation chains side by side.
 B2_CX int w_mel_len(int m) { const int t[80] = kWMelLen_INIT; return t[m]; }
 B2_CX int w_mel_off(int m) { const int t[80] = kWMelOff_INIT; return t[m]; }
-// the generated table names the tap's bin by (k1, k2) as k1*26 + 2*k2; the power buffer row is k2*16 + k1
-B2_CX int w_mel_row(int i) { const int t[B200MEL_W_NNZ] = kWMelRow_INIT; return ((t[i] % 26) / 2) * 16 + t[i] / 26; }
+B2_CX int w_mel_start(int m) { const int t[80] = kWMelStart_INIT; return t[m]; }
 B2_CX float w_mel_wt(int i) { const float t[B200MEL_W_NNZ] = kWMelW_INIT; return t[i]; }
+// power-buffer row of FFT bin k: pass-2 task k2 = k mod 25 (mirrored to <= 12) leaves bin k in row k2*16 + k1
+B2_CX int w_bin_row(int k) {
+  int k1 = k % 16, k2 = k % 25;
+  if (k2 > 12) { const int kk = 400 - k; k1 = kk % 16; k2 = kk % 25; }
+  return k2 * 16 + k1;
+}
+constexpr int W_MEL_FIXED_COST = 8;
+B2_CX int w_mel_total_cost() { int c = 0; for (int m = 0; m < 80; ++m) c += w_mel_len(m) + W_MEL_FIXED_COST; return c; }
+// first filter of warp w (w = 16 -> 80): the cumulative cost is cut into 16 equal shares
+B2_CX int w_mel_first(int w) {
+  if (w >= 16) return 80;
+  const int total = w_mel_total_cost();
+  int c = 0;
+  for (int m = 0; m < 80; ++m) {
+    if (c * 16 >= w * total) return m;
+    c += w_mel_len(m) + W_MEL_FIXED_COST;
+  }
+  return 80;
+}
 
-template <int I, int END>
-__device__ __forceinline__ void w_mel_taps(const float2* __restrict__ p_lane, float2& acc) {
-  if constexpr (I < END) {
-    constexpr int row = w_mel_row(I);
-    constexpr float wt = w_mel_wt(I);
-    acc = b2::vfmac(p_lane[row * 32], wt, acc);
-    w_mel_taps<I + 1, END>(p_lane, acc);
+template <int J, int LEN, int OFF, int REL, int NB>
+__device__ __forceinline__ void w_mel_taps(const float2 (&pb)[NB], float2& acc) {
+  if constexpr (J < LEN) {
+    constexpr float wt = w_mel_wt(OFF + J);
+    acc = (J == 0) ? b2::vmulc(pb[REL + J], wt) : b2::vfmac(pb[REL + J], wt, acc);
+    w_mel_taps<J + 1, LEN, OFF, REL, NB>(pb, acc);
   }
 }
 
-template <int M>
-__device__ __forceinline__ void w_mel_one(const float2* __restrict__ p_lane, float* __restrict__ out_col,
-                                          bool valid0, bool valid1, float& emax) {
-  constexpr int OFF = w_mel_off(M), LEN = w_mel_len(M);
-  float2 acc = make_float2(0.0f, 0.0f);
-  w_mel_taps<OFF, OFF + LEN>(p_lane, acc);
-  const float e0 = fmaxf(acc.x, 1e-10f), e1 = fmaxf(acc.y, 1e-10f);
-  if (valid0) { emax = fmaxf(emax, e0); out_col[(size_t)M * W_NFRAME] = w_norm_log(e0); }
-  if (valid1) { emax = fmaxf(emax, e1); out_col[(size_t)M * W_NFRAME + 8] = w_norm_log(e1); }
+template <int M, int FE, int BLO, int NB>
+__device__ __forceinline__ void w_mel_filters(const float2 (&pb)[NB], float* __restrict__ out_col,
+                                              bool valid0, bool valid1, float& emax) {
+  if constexpr (M < FE) {
+    float2 acc;
+    w_mel_taps<0, w_mel_len(M), w_mel_off(M), w_mel_start(M) - BLO, NB>(pb, acc);
+    const float e0 = fmaxf(acc.x, 1e-10f), e1 = fmaxf(acc.y, 1e-10f);
+    emax = fmaxf(emax, fmaxf(valid0 ? e0 : 0.0f, valid1 ? e1 : 0.0f));
+    const float y0 = w_norm_log(e0), y1 = w_norm_log(e1);
+    if (valid0) out_col[(size_t)M * W_NFRAME] = y0;
+    if (valid1) out_col[(size_t)M * W_NFRAME + 8] = y1;
+    w_mel_filters<M + 1, FE, BLO, NB>(pb, out_col, valid0, valid1, emax);
+  }
 }
 
 template <int W>
 __device__ __forceinline__ void w_mel_warp(const float2* __restrict__ p_lane, float* __restrict__ out_col,
                                            bool valid0, bool valid1, float& emax) {
-  w_mel_one<W>(p_lane, out_col, valid0, valid1, emax);
-  w_mel_one<W + 16>(p_lane, out_col, valid0, valid1, emax);
-  w_mel_one<W + 32>(p_lane, out_col, valid0, valid1, emax);
-  w_mel_one<W + 48>(p_lane, out_col, valid0, valid1, emax);
-  w_mel_one<W + 64>(p_lane, out_col, valid0, valid1, emax);
+  constexpr int FB = w_mel_first(W), FE = w_mel_first(W + 1);
+  static_assert(FE > FB, "every warp needs at least one filter");
+  constexpr int BLO = w_mel_start(FB), BHI = w_mel_start(FE - 1) + w_mel_len(FE - 1);
+  constexpr int NB = BHI - BLO;
+  float2 pb[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) pb[k] = p_lane[w_bin_row(BLO + k) * 32];
+  w_mel_filters<FB, FE, BLO, NB>(pb, out_col, valid0, valid1, emax);
 }
 
 // ---- mel + log + per-clip max for one tile whose power spectrum sits in P ------------------------
