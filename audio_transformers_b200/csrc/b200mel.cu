@@ -187,14 +187,22 @@ __device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_l
     w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
   }
   b2::real_dft25(x, w, o);
-  e_dst[0] = o[0];
-  e_dst[32] = make_float2(0.0f, 0.0f);    // Im X0 = 0 keeps pass 2 free of special cases
+  e_dst[0] = o[0];                        // X0 is real: row 1 (its imaginary part) is never read
 #pragma unroll
   for (int c = 1; c < 25; ++c) e_dst[(c + 1) * 32] = o[c];
 }
 
 // ---- pass 2: complex 16-point DFT for k2 (warp-uniform, runtime); |X|^2 written back in place ----
 __device__ __forceinline__ void w_pass2(int k2, const float2* __restrict__ e_lane, float2* __restrict__ p_lane) {
+  if (k2 == 0) {                              // the pass-1 outputs for k2 = 0 are real: half the work
+    float2 y[16], P[9];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) y[a] = e_lane[a * W_EBLK];
+    b2::real_dft16_power(y, P);
+#pragma unroll
+    for (int k1 = 0; k1 < 9; ++k1) p_lane[k1 * 32] = P[k1];   // |X[16-k1]| = |X[k1]|: rows 0..8 cover the task
+    return;
+  }
   float2 yr[16], yi[16], Xr[16], Xi[16];
   const float2* base = e_lane + k2 * 64;      // rows a*26 + 2*k2 (re) and a*26 + 2*k2 + 1 (im)
   float2* dst = p_lane + k2 * (16 * 32);      // power rows k2*16 + k1
@@ -220,6 +228,7 @@ B2_CX float w_mel_wt(int i) { const float t[B200MEL_W_NNZ] = kWMelW_INIT; return
 B2_CX int w_bin_row(int k) {
   int k1 = k % 16, k2 = k % 25;
   if (k2 > 12) { const int kk = 400 - k; k1 = kk % 16; k2 = kk % 25; }
+  if (k2 == 0 && k1 > 8) k1 = 16 - k1;        // real task: only k1 = 0..8 are stored
   return k2 * 16 + k1;
 }
 constexpr int W_MEL_FIXED_COST = 8;

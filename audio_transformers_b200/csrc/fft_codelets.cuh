@@ -256,6 +256,45 @@ B2_HD void cplx_dft16(const V yr[16], const V yi[16], V Xr[16], V Xi[16]) {
   }
 }
 
+// ---- 8-point DFT of REAL input, outputs k = 0..4 -------------------------------------------------
+// X0, X4 real; X1, X2, X3 complex (Xr, Xi); X[8-k] = conj X[k].
+template <class V>
+B2_HD void rdft8(const V x[8], V& X0, V& X4, V& X1r, V& X1i, V& X2r, V& X2i, V& X3r, V& X3i) {
+  typedef typename real_t<V>::type R;
+  V s04 = vadd(x[0], x[4]), d04 = vsub(x[0], x[4]), s26 = vadd(x[2], x[6]), d26 = vsub(x[2], x[6]);
+  V s15 = vadd(x[1], x[5]), d15 = vsub(x[1], x[5]), s37 = vadd(x[3], x[7]), d37 = vsub(x[3], x[7]);
+  V ee = vadd(s04, s26), eo = vadd(s15, s37);
+  X0 = vadd(ee, eo); X4 = vsub(ee, eo);
+  X2r = vsub(s04, s26); X2i = vsub(s37, s15);
+  V p = vsub(d15, d37), q = vadd(d15, d37);
+  X1r = vfmac(p, (R)B2_SQRT1_2, d04);  X1i = vneg(vfmac(q, (R)B2_SQRT1_2, d26));
+  X3r = vfmac(p, (R)-B2_SQRT1_2, d04); X3i = vfmac(q, (R)-B2_SQRT1_2, d26);
+}
+
+// ---- |X[k]|^2, k = 0..8, of the 16-point DFT of REAL input --------------------------------------
+// (pass 2 of the Whisper frame for k2 = 0, where the pass-1 outputs are real).  Even/odd split:
+// X[k] = E[k] + W16^k O[k], X[8-k] = conj(E[k] - W16^k O[k]) for k = 1..3.
+template <class V>
+B2_HD void real_dft16_power(const V y[16], V P[9]) {
+  typedef typename real_t<V>::type R;
+  V e[8], o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { e[j] = y[2 * j]; o[j] = y[2 * j + 1]; }
+  V E0, E4, E1r, E1i, E2r, E2i, E3r, E3i, O0, O4, O1r, O1i, O2r, O2i, O3r, O3i;
+  rdft8(e, E0, E4, E1r, E1i, E2r, E2i, E3r, E3i);
+  rdft8(o, O0, O4, O1r, O1i, O2r, O2i, O3r, O3i);
+  V x0 = vadd(E0, O0), x8 = vsub(E0, O0);
+  P[0] = vmul(x0, x0); P[8] = vmul(x8, x8);
+  P[4] = vfma(E4, E4, vmul(O4, O4));                 // X4 = E4 - i O4
+  twiddle16<1>(O1r, O1i); twiddle16<2>(O2r, O2i); twiddle16<3>(O3r, O3i);
+  { V ar = vadd(E1r, O1r), ai = vadd(E1i, O1i), br = vsub(E1r, O1r), bi = vsub(E1i, O1i);
+    P[1] = vfma(ar, ar, vmul(ai, ai)); P[7] = vfma(br, br, vmul(bi, bi)); }
+  { V ar = vadd(E2r, O2r), ai = vadd(E2i, O2i), br = vsub(E2r, O2r), bi = vsub(E2i, O2i);
+    P[2] = vfma(ar, ar, vmul(ai, ai)); P[6] = vfma(br, br, vmul(bi, bi)); }
+  { V ar = vadd(E3r, O3r), ai = vadd(E3i, O3i), br = vsub(E3r, O3r), bi = vsub(E3i, O3i);
+    P[3] = vfma(ar, ar, vmul(ai, ai)); P[5] = vfma(br, br, vmul(bi, bi)); }
+}
+
 // multiply (r + i m) by exp(-2 pi i E / 32), E compile-time (even E reuse the /16 table)
 #define B2_C32_1 0.98078528040323044913
 #define B2_S32_1 0.19509032201612826785
