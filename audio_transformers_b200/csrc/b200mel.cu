@@ -177,16 +177,42 @@ __device__ __forceinline__ void w_pass1(int a, const float* __restrict__ audio_l
     off[4 * q] = v.x; off[4 * q + 1] = v.y; off[4 * q + 2] = v.z; off[4 * q + 3] = v.w;
   }
 #pragma unroll
-  for (int b = 0; b < 25; ++b) {
-    const float* p = audio_lane + off[b];
-    x[b] = make_float2(p[0], p[W_LANE2]);
-  }
-#pragma unroll
   for (int q = 0; q < 7; ++q) {
     const float4 v = win4[q];
     w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
   }
+#if W_P1_STREAM
+  // The first stage is five independent 5-point transforms on inputs {r, r+5, .., r+20}.  Their audio loads are
+  // issued two groups ahead of the arithmetic instead of all up front, so that the shared-memory traffic of
+  // the 16 warps is spread over the phase instead of arriving as one burst at its start.
+  float2 Y0[5], Y1r[5], U1[5], Y2r[5], U2[5];
+  auto load_group = [&](int r) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float* p = audio_lane + off[r + 5 * j];
+      x[r + 5 * j] = make_float2(p[0], p[W_LANE2]);
+    }
+  };
+  load_group(0);
+  load_group(1);
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    b2::rdft5w(x[r], x[r + 5], x[r + 10], x[r + 15], x[r + 20], w[r], w[r + 5], w[r + 10], w[r + 15], w[r + 20],
+               Y0[r], Y1r[r], U1[r], Y2r[r], U2[r]);
+    if (r + 2 < 5) {
+      asm volatile("" : "+f"(Y0[r].x) :: "memory");   // pins the next loads behind this group's arithmetic
+      load_group(r + 2);
+    }
+  }
+  b2::real_dft25_stage2(Y0, Y1r, U1, Y2r, U2, o);
+#else
+#pragma unroll
+  for (int b = 0; b < 25; ++b) {
+    const float* p = audio_lane + off[b];
+    x[b] = make_float2(p[0], p[W_LANE2]);
+  }
   b2::real_dft25(x, w, o);
+#endif
   e_dst[0] = o[0];                        // X0 is real: row 1 (its imaginary part) is never read
 #pragma unroll
   for (int c = 1; c < 25; ++c) e_dst[(c + 1) * 32] = o[c];
@@ -320,6 +346,10 @@ __device__ long long* g_trace = nullptr;     // [iter][4 marks][16 warps] clock6
 #define W_MARK(k) do { if (blockIdx.x == 0 && lane == 0 && it < 32 && g_trace) g_trace[(it * 4 + (k)) * 16 + warp] = clock64(); } while (0)
 #else
 #define W_MARK(k) do { } while (0)
+#endif
+
+#ifndef W_P1_STREAM
+#define W_P1_STREAM 1
 #endif
 
 #ifndef W_MEL_FIRST_MASK

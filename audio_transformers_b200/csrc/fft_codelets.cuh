@@ -143,13 +143,9 @@ B2_HD void cdft5(const V zr[5], const V zi[5], V Yr[5], V Yi[5]) {
 // ---- 25-point DFT of REAL (windowed) input, outputs k = 0..12 ----------------------------------
 // x[b], b = 0..24 in natural DFT order; w[b] the window taps for those samples.
 // out[0] = X0 (real); out[2k-1] = Re X_k, out[2k] = Im X_k for k = 1..12.
-template <class V, class W>
-B2_HD void real_dft25(const V x[25], const W w[25], V out[25]) {
-  V Y0[5], Y1r[5], U1[5], Y2r[5], U2[5];
-#pragma unroll
-  for (int r = 0; r < 5; ++r)
-    rdft5w(x[r], x[r + 5], x[r + 10], x[r + 15], x[r + 20], w[r], w[r + 5], w[r + 10], w[r + 15], w[r + 20],
-           Y0[r], Y1r[r], U1[r], Y2r[r], U2[r]);
+// second stage, given the five first-stage 5-point transforms (see real_dft25)
+template <class V>
+B2_HD void real_dft25_stage2(const V Y0[5], const V Y1r[5], const V U1[5], const V Y2r[5], const V U2[5], V out[25]) {
   // s = 0: real 5-point DFT of Y0 -> X0, X5, X10
   {
     V y0, y1r, u1, y2r, u2;
@@ -194,6 +190,16 @@ B2_HD void real_dft25(const V x[25], const W w[25], V out[25]) {
     out[2 * 8 - 1] = Xr[3];  out[2 * 8] = vneg(Xi[3]);   // X8 = conj X17
     out[2 * 3 - 1] = Xr[4];  out[2 * 3] = vneg(Xi[4]);   // X3 = conj X22
   }
+}
+
+template <class V, class W>
+B2_HD void real_dft25(const V x[25], const W w[25], V out[25]) {
+  V Y0[5], Y1r[5], U1[5], Y2r[5], U2[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+    rdft5w(x[r], x[r + 5], x[r + 10], x[r + 15], x[r + 20], w[r], w[r + 5], w[r + 10], w[r + 15], w[r + 20],
+           Y0[r], Y1r[r], U1[r], Y2r[r], U2[r]);
+  real_dft25_stage2(Y0, Y1r, U1, Y2r, U2, out);
 }
 
 // ---- 4-point complex DFT (in place on 4 re/im pairs) --------------------------------------------
