@@ -119,6 +119,25 @@ def test_live_hf_extractor(ops):
     assert err.max() <= TOL
 
 
+@pytest.mark.parametrize("stride", [480000, 480004, 500000, 20600, 20604, 31000, 284, 280])
+def test_tma_and_generic_staging_agree(ops, stride, monkeypatch):
+    """Interior tiles arrive through one TMA box per tile, edge tiles through ordinary stores into the same
+    layout.  Both must give the same bits for every row stride the ABI accepts (the tensor map's extents depend
+    on it; 20600/20604 straddle the first stride that has an interior tile at all, 284/280 the smallest map)."""
+    rng = np.random.default_rng(stride)
+    n = min(stride, 480000)
+    host = (0.1 * rng.standard_normal((3, stride))).astype(np.float32)
+    lens = torch.tensor([n, max(1, n - 777), max(1, n // 2)], dtype=torch.int32).cuda()
+    wave = torch.from_numpy(host).cuda()
+    a = ops.whisper_logmel(wave, lens).cpu().numpy()
+    monkeypatch.setenv("B200MEL_DEBUG_NO_TMA", "1")
+    b = ops.whisper_logmel(wave, lens).cpu().numpy()
+    monkeypatch.delenv("B200MEL_DEBUG_NO_TMA")
+    assert np.array_equal(a, b)
+    ref = O.whisper_logmel([host[i, :int(lens[i])] for i in range(3)])
+    assert np.abs(a - ref).max() <= TOL
+
+
 def test_frame_mask(ops):
     lens = torch.tensor([1, 160, 161, 480000, 600000], dtype=torch.int32).cuda()
     m = ops.whisper_frame_mask(lens).cpu().numpy()
