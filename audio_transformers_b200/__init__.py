@@ -6,16 +6,16 @@ and every entry point fails loudly when it (or a CUDA device) is missing.  See D
 """
 __version__ = "0.1.0"
 
-__all__ = ["B200WhisperFeatureExtractor", "B200WhisperProcessor", "B200MelSpectrogram", "ops", "signals"]
+__all__ = ["B200WhisperFeatureExtractor", "B200WhisperProcessor", "B200MelSpectrogram", "B200UrbanFrontEnd", "ops", "signals"]
 
 
 def __getattr__(name):
     if name in ("B200WhisperFeatureExtractor", "B200WhisperProcessor"):
         from . import whisper
         return getattr(whisper, name)
-    if name == "B200MelSpectrogram":
-        from .urban import B200MelSpectrogram
-        return B200MelSpectrogram
+    if name in ("B200MelSpectrogram", "B200UrbanFrontEnd"):
+        from . import urban
+        return getattr(urban, name)
     if name in ("ops", "signals", "whisper", "urban", "collate"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")

@@ -589,6 +589,72 @@ urban_mel_kernel(const float* __restrict__ wave, long long stride, int n_samples
 }
 
 // ------------------------------------------------------------------------------------------------
+// Urban pre-steps (REF:urban_sounds/dataset.py:26-52, process_audio before the mel transform): mono mean,
+// torchaudio's sinc/Hann polyphase resampler (TA:functional/functional.py _get_sinc_resample_kernel /
+// _apply_sinc_resample_kernel: y[m*new + p] = sum_k kernel[p][k] * xpad[m*orig + k], xpad = x zero-padded by
+// `width` on the left), pad/trim to the target length and peak normalisation.
+// ------------------------------------------------------------------------------------------------
+constexpr int UP_THREADS = 256, UP_ITEMS = 4;
+
+__global__ void __launch_bounds__(UP_THREADS)
+urban_prep_kernel(const float* __restrict__ audio, long long in_stride, const int* __restrict__ in_lengths, int channels,
+                  int orig, int nw, const float* __restrict__ taps, int width,
+                  float* __restrict__ out, long long out_stride, int out_samples, unsigned int* __restrict__ clip_max_bits) {
+  const int clip = blockIdx.y;
+  const float* __restrict__ src = audio + (size_t)clip * (size_t)channels * (size_t)in_stride;
+  long long L = in_lengths ? (long long)in_lengths[clip] : in_stride;
+  L = L < 0 ? 0 : (L > in_stride ? in_stride : L);
+  const long long resampled = (L * nw + orig - 1) / orig;            // ceil(new * L / orig)
+  const int ktaps = 2 * width + orig;
+  const float inv_ch = 1.0f / (float)channels;
+  float amax = 0.0f;
+#pragma unroll
+  for (int it = 0; it < UP_ITEMS; ++it) {
+    const int j = (blockIdx.x * UP_ITEMS + it) * UP_THREADS + threadIdx.x;
+    if (j >= out_samples) continue;
+    float y = 0.0f;
+    if (j < resampled) {
+      if (orig == nw) {                                              // Resample is skipped when the rates agree
+        float sacc = 0.0f;
+        for (int c = 0; c < channels; ++c) sacc += __ldg(src + (size_t)c * in_stride + j);
+        y = channels > 1 ? sacc * inv_ch : sacc;
+      } else {
+        const int m = j / nw, p = j - m * nw;
+        const float* __restrict__ kp = taps + (size_t)p * ktaps;
+        const long long i0 = (long long)m * orig - width;            // first input sample under the filter
+        int k0 = i0 < 0 ? (int)(-i0) : 0;
+        int k1 = (i0 + ktaps > L) ? (int)(L - i0) : ktaps;
+        float acc = 0.0f;
+        if (channels == 1) {
+          for (int k = k0; k < k1; ++k) acc = __fmaf_rn(__ldg(kp + k), __ldg(src + i0 + k), acc);
+        } else {
+          for (int k = k0; k < k1; ++k) {
+            float sacc = 0.0f;
+            for (int c = 0; c < channels; ++c) sacc += __ldg(src + (size_t)c * in_stride + i0 + k);
+            acc = __fmaf_rn(__ldg(kp + k), sacc * inv_ch, acc);
+          }
+        }
+        y = acc;
+      }
+    }
+    out[(size_t)clip * out_stride + j] = y;
+    amax = fmaxf(amax, fabsf(y));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(amax));
+}
+
+__global__ void __launch_bounds__(UP_THREADS)
+urban_peak_norm_kernel(float* __restrict__ out, long long out_stride, int out_samples, const unsigned int* __restrict__ clip_max_bits) {
+  const int clip = blockIdx.y;
+  const float m = __uint_as_float(clip_max_bits[clip]);
+  if (!(m > 0.0f)) return;                                           // REF:urban_sounds/dataset.py:51: only if there is sound
+  float* p = out + (size_t)clip * out_stride;
+  for (int j = blockIdx.x * UP_THREADS + threadIdx.x; j < out_samples; j += gridDim.x * UP_THREADS) p[j] = __fdiv_rn(p[j], m);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
@@ -796,6 +862,43 @@ int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples
   if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "urban_mel_kernel launch");
+  return B200MEL_OK;
+}
+
+size_t b200mel_urban_prep_workspace_bytes(const b200mel_handle* h, int32_t batch) {
+  if (!h || batch <= 0 || h->preset != B200MEL_PRESET_URBAN) return 0;
+  return ((size_t)batch * sizeof(unsigned int) + 255) & ~(size_t)255;
+}
+
+int b200mel_urban_prep_f32(b200mel_handle* h, const float* audio, int64_t in_stride, const int32_t* in_lengths,
+                           int32_t channels, int32_t batch, int32_t orig_freq, int32_t new_freq,
+                           const float* taps, int32_t width, float* out, int64_t out_stride, int32_t out_samples,
+                           void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!h || h->preset != B200MEL_PRESET_URBAN) return fail(B200MEL_ERR_BAD_ARG, "urban_prep: handle is not an urban-preset handle");
+  if (batch < 0) return fail(B200MEL_ERR_BAD_ARG, "urban_prep: negative batch");
+  if (batch == 0) return B200MEL_OK;
+  if (!audio || !out) return fail(B200MEL_ERR_BAD_ARG, "urban_prep: NULL audio/out");
+  if (channels < 1 || in_stride < 1 || out_samples < 1 || out_stride < out_samples)
+    return fail(B200MEL_ERR_BAD_ARG, "urban_prep: channels, in_stride, out_samples must be positive and out_stride >= out_samples");
+  if (orig_freq < 1 || new_freq < 1) return fail(B200MEL_ERR_BAD_ARG, "urban_prep: frequencies must be positive (pass them divided by their gcd)");
+  if (orig_freq != new_freq && (!taps || width < 1)) return fail(B200MEL_ERR_BAD_ARG, "urban_prep: resampling needs the tap table and its width");
+  if (!workspace || workspace_bytes < b200mel_urban_prep_workspace_bytes(h, batch))
+    return fail(B200MEL_ERR_WORKSPACE, "urban_prep: workspace too small (see b200mel_urban_prep_workspace_bytes)");
+  if (batch > 65535) return fail(B200MEL_ERR_BAD_ARG, "urban_prep: batch too large for one launch");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  unsigned int* clip_max = (unsigned int*)workspace;
+  cudaError_t e = cudaMemsetAsync(clip_max, 0, (size_t)batch * sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
+  const int per_block = UP_THREADS * UP_ITEMS;
+  dim3 grid((out_samples + per_block - 1) / per_block, batch);
+  urban_prep_kernel<<<grid, UP_THREADS, 0, stream>>>(audio, (long long)in_stride, in_lengths, channels, orig_freq, new_freq,
+                                                     taps, width, out, (long long)out_stride, out_samples, clip_max);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "urban_prep_kernel launch");
+  dim3 grid2(24, batch);
+  urban_peak_norm_kernel<<<grid2, UP_THREADS, 0, stream>>>(out, (long long)out_stride, out_samples, clip_max);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "urban_peak_norm_kernel launch");
   return B200MEL_OK;
 }
 

@@ -4,6 +4,7 @@ through its features: the extractor returns numpy, HF:models/whisper/feature_ext
     torch.ops.b200mel.whisper_logmel(wave, lengths) -> (B, 80, 3000) float32
     torch.ops.b200mel.whisper_frame_mask(lengths)   -> (B, 3000) int32
     torch.ops.b200mel.mel_power(wave, log_eps)       -> (B, 64, 1 + T // 512) float32
+    torch.ops.b200mel.urban_prep(audio, lengths, orig, new, taps, width, out_samples) -> (B, out_samples) float32
 
 All inputs and outputs live on the same CUDA device; the kernels are enqueued on the current
 stream of that device without any host synchronisation.
@@ -53,6 +54,8 @@ _LIBDEF = torch.library.Library("b200mel", "DEF")
 _LIBDEF.define("whisper_logmel(Tensor wave, Tensor? lengths) -> Tensor")
 _LIBDEF.define("whisper_frame_mask(Tensor lengths) -> Tensor")
 _LIBDEF.define("mel_power(Tensor wave, float log_eps) -> Tensor")
+_LIBDEF.define("urban_prep(Tensor audio, Tensor? lengths, int orig_freq, int new_freq, Tensor? taps, int width, "
+               "int out_samples) -> Tensor")
 
 
 def _whisper_logmel_cuda(wave: torch.Tensor, lengths: Optional[torch.Tensor]) -> torch.Tensor:
@@ -134,7 +137,47 @@ def _mel_power_cuda(wave: torch.Tensor, log_eps: float) -> torch.Tensor:
     return out
 
 
+def _urban_prep_cuda(audio: torch.Tensor, lengths: Optional[torch.Tensor], orig_freq: int, new_freq: int,
+                     taps: Optional[torch.Tensor], width: int, out_samples: int) -> torch.Tensor:
+    """(B, C, T) planar float32 -> (B, out_samples): mono mean, sinc resampling, pad/trim, peak normalisation."""
+    _require_cuda(audio, "audio")
+    if audio.dim() != 3 or audio.dtype != torch.float32:
+        raise ValueError("b200mel.urban_prep: audio must be a (B, C, T) float32 tensor")
+    audio = audio.contiguous()
+    batch, channels, t = audio.shape
+    if lengths is not None:
+        _require_cuda(lengths, "lengths")
+        if lengths.dtype != torch.int32 or lengths.shape != (batch,):
+            raise ValueError("b200mel.urban_prep: lengths must be an int32 tensor of shape (B,)")
+        lengths = lengths.contiguous()
+    if orig_freq != new_freq:
+        if taps is None:
+            raise ValueError("b200mel.urban_prep: resampling needs the tap table")
+        _require_cuda(taps, "taps")
+        if taps.dtype != torch.float32 or tuple(taps.shape) != (new_freq, 2 * width + orig_freq):
+            raise ValueError("b200mel.urban_prep: taps must be float32 of shape (new_freq, 2*width + orig_freq)")
+        taps = taps.contiguous()
+    out_stride = (out_samples + 3) // 4 * 4
+    out = torch.empty((batch, out_stride), dtype=torch.float32, device=audio.device)
+    if batch == 0:
+        return out[:, :out_samples]
+    lib = _lib.load()
+    h = _handle(audio.device, _lib.PRESET_URBAN)
+    ws_bytes = lib.b200mel_urban_prep_workspace_bytes(h, batch)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=audio.device)
+    with torch.cuda.device(audio.device):
+        st = lib.b200mel_urban_prep_f32(
+            h, ctypes.c_void_p(audio.data_ptr()), t, ctypes.c_void_p(lengths.data_ptr()) if lengths is not None else None,
+            channels, batch, int(orig_freq), int(new_freq),
+            ctypes.c_void_p(taps.data_ptr()) if (taps is not None and orig_freq != new_freq) else None, int(width),
+            ctypes.c_void_p(out.data_ptr()), out_stride, int(out_samples),
+            ctypes.c_void_p(ws.data_ptr()), ws_bytes, _stream_ptr(audio.device))
+    _lib.check(st, "b200mel_urban_prep_f32")
+    return out[:, :out_samples] if out_stride == out_samples else out[:, :out_samples]
+
+
 _LIBDEF.impl("whisper_logmel", _whisper_logmel_cuda, "CUDA")
+_LIBDEF.impl("urban_prep", _urban_prep_cuda, "CUDA")
 _LIBDEF.impl("whisper_frame_mask", _whisper_frame_mask_cuda, "CUDA")
 _LIBDEF.impl("mel_power", _mel_power_cuda, "CUDA")
 
@@ -152,6 +195,16 @@ def _whisper_frame_mask_fake(lengths):
 @torch.library.register_fake("b200mel::mel_power")
 def _mel_power_fake(wave, log_eps):
     return wave.new_empty((wave.shape[0], U_NMEL, 1 + wave.shape[1] // U_HOP), dtype=torch.float32)
+
+
+@torch.library.register_fake("b200mel::urban_prep")
+def _urban_prep_fake(audio, lengths, orig_freq, new_freq, taps, width, out_samples):
+    return audio.new_empty((audio.shape[0], out_samples), dtype=torch.float32)
+
+
+def urban_prep(audio: torch.Tensor, lengths: Optional[torch.Tensor], orig_freq: int, new_freq: int,
+               taps: Optional[torch.Tensor], width: int, out_samples: int) -> torch.Tensor:
+    return torch.ops.b200mel.urban_prep(audio, lengths, orig_freq, new_freq, taps, width, out_samples)
 
 
 def whisper_logmel(wave: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -76,3 +76,39 @@ def urban_batch(batch: int = 32, seed: int = 0, n_samples: int = URBAN_SAMPLES) 
     x = rng.standard_normal((batch, 1, n_samples)).astype(np.float32)
     x /= np.abs(x).max(axis=-1, keepdims=True)
     return x
+
+
+# Raw decoded clips for the urban pre-steps (REF:urban_sounds/dataset.py:64-68 hands `audio['array']` and
+# `audio['sampling_rate']` to process_audio).  (name, sampling rate, channels, samples per channel):
+# UrbanSound8K mixes rates and channel counts, clips are <= 4 s.
+URBAN_PREP_CASES = (
+    ("stereo_44k1_4s", 44100, 2, 176400),
+    ("mono_44k1_short", 44100, 1, 61234),
+    ("stereo_48k_4s", 48000, 2, 192000),
+    ("mono_48k_long", 48000, 1, 250000),       # longer than 4 s after resampling: trimmed
+    ("mono_22k05_full", 22050, 1, 88200),      # no resampling
+    ("stereo_22k05_short", 22050, 2, 40000),
+    ("mono_16k", 16000, 1, 50000),             # upsampling
+    ("mono_8k_tiny", 8000, 1, 2000),
+    ("stereo_96k", 96000, 2, 300000),
+    ("mono_11k025", 11025, 1, 44100),
+    ("silence_44k1", 44100, 2, 30000),         # all zeros: no normalisation
+)
+
+
+def urban_raw_clip(name: str, rate: int, channels: int, n_in: int) -> np.ndarray:
+    """float64 array shaped like `datasets` decodes it: (n,) for mono, (channels, n) otherwise.  Band-limited
+    tones plus noise at an arbitrary scale, so that resampling, the mono mean and the peak normalisation all
+    have something to do."""
+    seed = sum(ord(c) for c in name)
+    rng = np.random.default_rng([seed, rate, channels])
+    if name.startswith("silence"):
+        x = np.zeros((channels, n_in), dtype=np.float64)
+    else:
+        t = np.arange(n_in, dtype=np.float64) / rate
+        x = np.empty((channels, n_in), dtype=np.float64)
+        for c in range(channels):
+            f1, f2 = 220.0 * (c + 1), min(0.18 * rate, 3100.0 + 400.0 * c)
+            x[c] = 0.31 * np.sin(2 * np.pi * f1 * t + c) + 0.12 * np.sin(2 * np.pi * f2 * t) + 0.05 * rng.standard_normal(n_in)
+        x *= 0.37
+    return x[0] if channels == 1 else x

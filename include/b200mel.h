@@ -16,6 +16,8 @@
  *   b200mel_mel_f32              TA:transforms/_transforms.py:621-631 (MelSpectrogram.forward ->
  *                                Spectrogram -> MelScale) plus REF:urban_sounds/dataset.py:56
  *                                (torch.log(mel + 1e-9)), as built at REF:urban_sounds/dataset.py:19-24.
+ *   b200mel_urban_prep_f32       REF:urban_sounds/dataset.py:26-52 (mono mean, T.Resample, pad/trim, peak
+ *                                normalisation ahead of the mel transform).
  *   b200mel_get_table            the construction-time constants of both call sites
  *                                (HF:audio_utils.py:453-544 mel_filter_bank; TA:functional/
  *                                functional.py:518-587 melscale_fbanks; torch.hann_window).
@@ -105,6 +107,24 @@ int b200mel_whisper_frame_mask(b200mel_handle* h, const int32_t* lengths, int32_
  */
 int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples, int32_t n_samples,
                     int32_t batch, float log_eps, float* out, void* stream);
+
+/* Urban preset, the steps of REF:urban_sounds/dataset.py:26-52 (process_audio) that precede the mel transform:
+ * mono mean over the channels (:31-34), torchaudio's sinc/Hann resampler orig_freq -> new_freq (:37-39;
+ * TA:functional/functional.py _get_sinc_resample_kernel / _apply_sinc_resample_kernel), zero pad / trim to
+ * out_samples (:42-48) and division by the clip's max |x| when that is > 0 (:51-52).
+ *   audio        [batch][channels][in_stride] float32 (planar); in_lengths[batch] int32 valid samples per
+ *                channel, or NULL meaning in_stride.
+ *   orig_freq, new_freq   the two rates divided by their gcd; equal values skip the resampler.
+ *   taps         [new_freq][2*width + orig_freq] float32 device table built by the caller with torchaudio's
+ *                formula (audio_transformers_b200/urban.py: sinc_resample_kernel); NULL when the rates agree.
+ *   out          [batch][out_stride] float32, out_samples written per clip.
+ *   workspace    b200mel_urban_prep_workspace_bytes(h, batch) bytes, no initialisation needed.
+ */
+size_t b200mel_urban_prep_workspace_bytes(const b200mel_handle* h, int32_t batch);
+int b200mel_urban_prep_f32(b200mel_handle* h, const float* audio, int64_t in_stride, const int32_t* in_lengths,
+                           int32_t channels, int32_t batch, int32_t orig_freq, int32_t new_freq,
+                           const float* taps, int32_t width, float* out, int64_t out_stride, int32_t out_samples,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* Optional per-kernel timing for benchmarks: between profile_begin and profile_end every call on
  * this handle brackets its dominant kernel (the fused log-mel kernel, not the memset / clamp pass)

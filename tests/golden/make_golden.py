@@ -110,6 +110,35 @@ def main() -> None:
     )
     print("urban", tuple(logmel.shape), float(logmel.max()), float(logmel.min()), float(z.min()))
 
+    # ---- Urban pre-steps: REF:urban_sounds/dataset.py:26-58 process_audio, restated with the same torch /
+    # torchaudio calls (the class itself cannot be built offline: its __init__ downloads the dataset) ----
+    import torchaudio.transforms as T
+
+    def process_audio(audio_array, orig_sr, sr=22050, target_length=88200):
+        waveform = torch.from_numpy(audio_array).float()
+        waveform = waveform.mean(dim=0, keepdim=True) if len(waveform.shape) > 1 else waveform.unsqueeze(0)
+        if orig_sr != sr:
+            waveform = T.Resample(orig_sr, sr)(waveform)
+        if waveform.shape[1] < target_length:
+            waveform = torch.nn.functional.pad(waveform, (0, target_length - waveform.shape[1]))
+        else:
+            waveform = waveform[:, :target_length]
+        if torch.max(torch.abs(waveform)) > 0:
+            waveform = waveform / torch.max(torch.abs(waveform))
+        return waveform, torch.log(mel_tf(waveform) + 1e-9)
+
+    prep = {"versions": np.array(repr(versions)), "names": np.array([c[0] for c in signals.URBAN_PREP_CASES])}
+    for name, rate, channels, n_in in signals.URBAN_PREP_CASES:
+        audio = signals.urban_raw_clip(name, rate, channels, n_in)
+        with torch.no_grad():
+            wav, lm = process_audio(audio, rate)
+        prep[f"{name}/meta"] = np.array([rate, channels, n_in], dtype=np.int64)
+        prep[f"{name}/wave_sub"] = wav.numpy()[0, ::37].copy()
+        prep[f"{name}/wave_stats"] = np.array([wav.double().sum().item(), wav.abs().max().item()], dtype=np.float64)
+        prep[f"{name}/logmel_sub"] = lm.numpy()[0, :, ::9].copy()
+        print(f"urban prep {name:16s} rate={rate} ch={channels} n={n_in} wave sum={prep[f'{name}/wave_stats'][0]:+.4f}")
+    np.savez_compressed(os.path.join(OUT, "urban_prep_golden.npz"), **prep)
+
 
 if __name__ == "__main__":
     main()

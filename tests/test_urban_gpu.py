@@ -91,6 +91,36 @@ def test_module_matches_live_torchaudio(ops):
     assert torch.equal(one, mine(wave.cuda())[0])
 
 
+def test_prep_front_end_vs_golden_and_oracle(ops, golden_dir):
+    """REF:urban_sounds/dataset.py:26-58 (process_audio) on the GPU, batched over mixed rates and channel counts,
+    against the torch/torchaudio golden vectors and the oracle."""
+    from audio_transformers_b200.urban import B200UrbanFrontEnd
+    g = np.load(os.path.join(golden_dir, "urban_prep_golden.npz"))
+    names = [str(n) for n in g["names"]]
+    metas = [tuple(int(v) for v in g[f"{n}/meta"]) for n in names]
+    arrays = [signals.urban_raw_clip(n, *m) for n, m in zip(names, metas)]
+    rates = [m[0] for m in metas]
+    fe = B200UrbanFrontEnd()
+    waves = fe.waveforms(arrays, rates)
+    assert waves.shape == (len(names), 88200) and waves.is_cuda and waves.dtype == torch.float32
+    feats = fe.process_batch(arrays, rates)
+    assert feats.shape == (len(names), 1, 64, 173) and feats.is_cuda
+    w, f = waves.cpu().numpy(), feats.cpu().numpy()
+    for i, name in enumerate(names):
+        assert np.abs(w[i, ::37] - g[f"{name}/wave_sub"]).max() <= 2e-6, name
+        assert abs(float(np.abs(w[i]).max()) - g[f"{name}/wave_stats"][1]) <= 1e-6, name
+        ref_w = O.urban_preprocess(arrays[i], orig_sr=rates[i])
+        assert np.abs(w[i] - ref_w[0]).max() <= 2e-6, name
+        ref = g[f"{name}/logmel_sub"]
+        lm = f[i, 0][:, ::9]
+        strong = (ref > ref.max() - 9.2) & (ref > np.log(1e-6))      # see tests/test_oracle.py::_strong
+        assert np.abs(lm[strong] - ref[strong]).max(initial=0.0) <= TOL, name
+        assert np.abs(np.exp(lm) - np.exp(ref)).max() <= 1e-5 * np.exp(ref).max() + 1e-9, name
+    # the reference's per-sample signature
+    one = fe.process_audio(arrays[0], rates[0])
+    assert one.shape == (1, 64, 173) and torch.equal(one, feats[0])
+
+
 def test_errors(ops):
     from audio_transformers_b200 import B200MelSpectrogram
     with pytest.raises(NotImplementedError):
