@@ -213,6 +213,45 @@ class B200WhisperFeatureExtractor:
         return _batch_feature(data)
 
 
+    # -- segment mode --------------------------------------------------------------------------------
+    def segment_features(self, raw_speech, segment_samples: int, sampling_rate: Optional[int] = None,
+                         device: Union[str, torch.device, None] = None) -> torch.Tensor:
+        """Features of consecutive segments of ONE clip, each padded to 30 s, in a single launch.
+
+        REF:whisper_finetune/inference.py:176-200 cuts the upload into ``segment_duration``-second pieces and calls
+        the processor once per piece (so each piece is right-padded with zeros to 30 s).  Here the clip crosses
+        PCIe once and the pieces are rows of a strided view of that one device buffer (row stride =
+        ``segment_samples``, per-row lengths), so no padded copy is ever materialised.  Returns
+        ``(ceil(N / segment_samples), 80, 3000)`` float32 on the GPU; an empty clip gives ``(0, 80, 3000)``."""
+        if sampling_rate is not None and sampling_rate != self.sampling_rate:
+            raise ValueError(
+                f"The model corresponding to this feature extractor: {_CLASS_NAME} was trained using a"
+                f" sampling rate of {self.sampling_rate}. Please make sure that the provided `raw_speech` input"
+                f" was sampled with {self.sampling_rate} and not {sampling_rate}.")
+        if segment_samples <= 0 or segment_samples % 4 != 0 or segment_samples > self.n_samples:
+            raise ValueError(f"segment_samples must be a positive multiple of 4 and at most {self.n_samples}")
+        if isinstance(raw_speech, torch.Tensor):
+            clip = raw_speech.detach().to(torch.float32).reshape(-1)
+            dev = self._target_device(clip.device if clip.is_cuda else device)
+        else:
+            a = np.asarray(raw_speech, dtype=np.float32)
+            if a.ndim != 1:
+                raise ValueError(f"Only mono-channel audio is supported for input to {_CLASS_NAME}")
+            clip = torch.from_numpy(np.ascontiguousarray(a))
+            dev = self._target_device(device)
+        n = int(clip.shape[0])
+        k = (n + segment_samples - 1) // segment_samples
+        if k == 0:
+            return torch.empty((0, self.feature_size, self.nb_max_frames), dtype=torch.float32, device=dev)
+        buf = torch.empty((k * segment_samples + 4,), dtype=torch.float32, device=dev)   # +4: TMA boxes are 16-byte granular
+        buf[:n].copy_(clip if clip.is_cuda else clip.pin_memory(), non_blocking=True)
+        buf[n:].zero_()
+        lens = torch.full((k,), segment_samples, dtype=torch.int32)
+        lens[-1] = n - (k - 1) * segment_samples
+        rows = buf[:k * segment_samples].view(k, segment_samples)
+        return ops.whisper_logmel(rows, lens.to(dev, non_blocking=True))
+
+
 class B200WhisperProcessor:
     """``WhisperProcessor`` look-alike: audio goes to the B200 extractor, everything else
     (``tokenizer``, ``decode``, ``batch_decode``, ``save_pretrained``, ...) to the wrapped objects.

@@ -100,6 +100,22 @@ def test_segment_chunks_like_inference(ops):
     assert np.abs(out - ref).max() <= TOL
 
 
+def test_segment_features_zero_copy(ops):
+    """The segment mode of the shim (one H2D, strided rows, one launch) equals the per-piece calls of the reference."""
+    from audio_transformers_b200 import B200WhisperFeatureExtractor
+    fe = B200WhisperFeatureExtractor(device="cuda")
+    for n in (480000, 333333, 80000, 79999, 5, 700001):
+        clip = signals.whisper_clip(3, seed=12, n_samples=n)
+        seg = fe.segment_features(clip, 80000, sampling_rate=16000)
+        chunks = [clip[i:i + 80000] for i in range(0, n, 80000)]
+        assert seg.shape == (len(chunks), 80, 3000) and seg.is_cuda
+        assert np.array_equal(seg.cpu().numpy(), _run(ops, chunks))
+        assert np.abs(seg.cpu().numpy() - O.whisper_logmel(chunks)).max() <= TOL
+    assert fe.segment_features(np.zeros(0, np.float32), 80000).shape == (0, 80, 3000)
+    with pytest.raises(ValueError):
+        fe.segment_features(np.zeros(10, np.float32), 80000, sampling_rate=8000)
+
+
 def test_batch_independence_and_determinism(ops):
     clips = [signals.whisper_clip(i, seed=4) for i in range(5)]
     a = _run(ops, clips)
