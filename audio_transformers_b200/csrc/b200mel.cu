@@ -594,6 +594,13 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
   if (lane == 0 && emax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(emax));
 }
 
+#ifndef V_ROTATE
+#define V_ROTATE 1
+#endif
+#ifndef V_MEL_FIRST
+#define V_MEL_FIRST(w) (((w) >> 2) & 1)
+#endif
+
 __global__ void __launch_bounds__(V_THREADS, 2)
 whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
                         const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
@@ -617,9 +624,13 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
   const float* audio_lane = s_audio + (16 * (warp >> 2) + (lane & 7)) * W_PITCH;
   float2* p1_dst = s_e + p1_a * V_EBLK + 8 * (warp >> 2) + (lane & 7);
   // pass-2 role: warps 0..5 take tasks k2 = 1 + 2 warp + lane / 16, warp 6 the real task k2 = 0 (lanes 0..15), warp 7 none
+  // The second CTA of an SM (CTAs are dealt round-robin, so blockIdx >= gridDim / 2) rotates the roles by two warps:
+  // the light pass-2 warps (real task, idle) then sit on the schedulers that carry two full tasks in the first CTA.
+  const int rot = (V_ROTATE && blockIdx.x >= (gridDim.x >> 1)) ? 2 : 0;
+  const int p2_warp = (warp + rot) & 7;
   const int p2_col = lane & 15;
-  const int p2_k2 = 1 + 2 * warp + (lane >> 4);
-  const bool mel_first = (warp >> 1) & 1;
+  const int p2_k2 = 1 + 2 * p2_warp + (lane >> 4);
+  const bool mel_first = V_MEL_FIRST(warp);
   constexpr int STAGE_TID = 7 * 32;
 
   auto stage = [&](int t) -> bool {
@@ -664,8 +675,8 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
       const int next = tile + gridDim.x;
       cur_tma = (next < ntiles) ? stage(next) : false;
     }
-    if (warp < 6) v_pass2(p2_k2, s_e + p2_col, s_p + p2_col);
-    else if (warp == 6 && lane < 16) v_pass2_real(s_e + p2_col, s_p + p2_col);
+    if (p2_warp < 6) v_pass2(p2_k2, s_e + p2_col, s_p + p2_col);
+    else if (p2_warp == 6 && lane < 16) v_pass2_real(s_e + p2_col, s_p + p2_col);
     prev_clip = tile / V_TILES_PER_CLIP;
     prev_f0 = (tile - prev_clip * V_TILES_PER_CLIP) * V_TILE;
   }
