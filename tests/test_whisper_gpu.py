@@ -116,6 +116,24 @@ def test_segment_features_zero_copy(ops):
         fe.segment_features(np.zeros(10, np.float32), 80000, sampling_rate=8000)
 
 
+def test_collated_batch_path(ops):
+    """__getitem__ keeps the waveform, the collate stacks the ragged clips into one pinned
+    buffer, features_on_device does one H2D and one launch (replaces REF:whisper_finetune/dataset.py:53-110)."""
+    from audio_transformers_b200 import B200WhisperFeatureExtractor
+    from audio_transformers_b200.collate import WaveformCollator, features_on_device
+    lens = (480000, 91234, 16000, 520000)
+    items = [{"waveform": signals.whisper_clip(i, seed=8, n_samples=n), "labels": torch.arange(3 + i),
+              "emotion_label": i % 3} for i, n in enumerate(lens)]
+    batch = WaveformCollator(pad_token_id=50257)(items)
+    assert batch["waveform"].is_pinned() and batch["waveform"].shape == (4, 480000) and batch["labels"].shape == (4, 6)
+    out = features_on_device(batch, B200WhisperFeatureExtractor(device="cuda"))
+    feats = out["input_features"]
+    assert feats.is_cuda and feats.shape == (4, 80, 3000)
+    assert feats.to("cuda") is feats                                   # REF:whisper_finetune/train.py:188 becomes a no-op
+    ref = O.whisper_logmel([it["waveform"] for it in items])
+    assert np.abs(feats.cpu().numpy() - ref).max() <= TOL
+
+
 def test_batch_independence_and_determinism(ops):
     clips = [signals.whisper_clip(i, seed=4) for i in range(5)]
     a = _run(ops, clips)
