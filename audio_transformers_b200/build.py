@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "b200mel.cu")
 OUT = os.path.join(HERE, "libb200mel.so")
-DEPS = [SRC, os.path.join(HERE, "csrc", "fft_codelets.cuh"), os.path.join(HERE, "csrc", "generated", "tables.inc"),
-        os.path.join(os.path.dirname(HERE), "include", "b200mel.h")]
+DEPS = ([SRC, os.path.join(HERE, "csrc", "generated", "tables.inc"), os.path.join(os.path.dirname(HERE), "include", "b200mel.h")]
+        + sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

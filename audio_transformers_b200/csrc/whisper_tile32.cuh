@@ -1,0 +1,245 @@
+// whisper_tile32.cuh -- the default Whisper kernel: 32-frame tiles, two CTAs per SM.
+#pragma once
+// ================================================================================================
+// Whisper kernel, 32-frame tiles, TWO CTAs per SM
+//
+// Same arithmetic and the same three stages as whisper_logmel_kernel, re-cut so that a tile needs 107 KB of
+// shared memory instead of 208 KB: two independent 256-thread CTAs share an SM, and while one waits at a block
+// barrier or on its shared-memory loads the other one computes.  (The 64-frame kernel is latency bound: 16 warps,
+// all in the same phase.)  What makes the half-size tile possible without giving up the packed f32x2 arithmetic:
+//   pass 1   a warp is 8 frame pairs x 4 classes anyway (w_pass1), so a 32-frame tile is simply 2 x 4 warp tasks;
+//   pass 2   the 16-point DFT is the same code for every k2 (no twiddles), so a warp takes 16 columns x 2 tasks;
+//   mel      a warp takes the 16 columns unpacked: lanes 0..15 the first frame of each pair, lanes 16..31 the
+//            second, scalar FFMA with the same immediates (the FMA pipe time per frame is unchanged).
+// ================================================================================================
+constexpr int V_TILE = 32, V_THREADS = 256, V_WARPS = 8;
+constexpr int V_TILES_PER_CLIP = (W_NFRAME + V_TILE - 1) / V_TILE;               // 94
+constexpr int V_ROWS = ((V_TILE - 1) * W_HOP + W_NFFT + W_HOP - 1) / W_HOP;      // 34
+constexpr int V_COLS = V_TILE / 2;                                               // 16 float2 columns
+constexpr int V_SM_AUDIO = ((V_ROWS * W_PITCH + 31) / 32) * 32;                  // floats
+constexpr int V_TX_BYTES = V_ROWS * W_PITCH * 4;
+constexpr int V_EBLK = 26 * V_COLS + 8;                                          // float2 per class block (+8: two classes of a half-warp store to different banks)
+constexpr int V_SM_E = 16 * V_EBLK * 2;                                          // floats
+constexpr int V_SM_P = W_PROWS * V_COLS * 2;                                     // floats
+constexpr int V_SMEM_BYTES = (V_SM_AUDIO + V_SM_E + V_SM_P + W_SM_TAB) * 4 + 16;
+static_assert(2 * (V_SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs must fit in one SM");
+
+__device__ __forceinline__ WTile v_tile(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
+                                        int tile, int use_tma) {
+  WTile t;
+  t.clip = tile / V_TILES_PER_CLIP;
+  t.f0 = (tile - t.clip * V_TILES_PER_CLIP) * V_TILE;
+  const long long len_ll = lengths ? (long long)__ldg(lengths + t.clip) : stride;
+  t.L = (int)(len_ll < 0 ? 0 : (len_ll > W_NSAMP ? W_NSAMP : len_ll));
+  t.src = wave + (size_t)t.clip * (size_t)stride;
+  const long long g0 = (long long)t.f0 * W_HOP - W_NFFT / 2;
+  t.tma = use_tma && g0 >= 0 && g0 + V_ROWS * W_HOP <= t.L && g0 + V_ROWS * W_HOP + 4 <= stride;
+  return t;
+}
+
+__device__ __forceinline__ void v_stage_generic(const WTile& t, float* __restrict__ s_audio, int part, int nparts, int lane) {
+  const int g0 = t.f0 * W_HOP - W_NFFT / 2;
+  for (int r = part; r < V_ROWS; r += nparts) {
+    float* d = s_audio + r * W_PITCH + lane;
+    const int gs = g0 + r * W_HOP + lane;
+#pragma unroll
+    for (int k = 0; k < W_HOP / 32; ++k) {
+      const int g = gs + 32 * k;
+      const int j = g < 0 ? -g : (g >= W_NSAMP ? 2 * (W_NSAMP - 1) - g : g);
+      d[32 * k] = (j >= 0 && j < t.L) ? __ldg(t.src + j) : 0.0f;
+    }
+  }
+}
+
+// pass 1: identical to w_pass1 but for the E layout of this kernel (16 columns per row)
+__device__ __forceinline__ void v_pass1(int a, const float* __restrict__ audio_lane, float2* __restrict__ e_dst,
+                                        const int* __restrict__ s_off, const float* __restrict__ s_win) {
+  float2 x[25], o[25];
+  int off[28];
+  float w[28];
+  const int4* off4 = reinterpret_cast<const int4*>(s_off + a * 28);
+  const float4* win4 = reinterpret_cast<const float4*>(s_win + a * 28);
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const int4 v = off4[q];
+    off[4 * q] = v.x; off[4 * q + 1] = v.y; off[4 * q + 2] = v.z; off[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const float4 v = win4[q];
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int b = 0; b < 25; ++b) {
+    const float* p = audio_lane + off[b];
+    x[b] = make_float2(p[0], p[W_LANE2]);
+  }
+  b2::real_dft25(x, w, o);
+  e_dst[0] = o[0];
+#pragma unroll
+  for (int c = 1; c < 25; ++c) e_dst[(c + 1) * V_COLS] = o[c];
+}
+
+// pass 2 for one (k2, column) per lane; k2 >= 1
+__device__ __forceinline__ void v_pass2(int k2, const float2* __restrict__ e_col, float2* __restrict__ p_col) {
+  float2 yr[16], yi[16], Xr[16], Xi[16];
+  const float2* base = e_col + k2 * (2 * V_COLS);
+#pragma unroll
+  for (int a = 0; a < 16; ++a) {
+    yr[a] = base[a * V_EBLK];
+    yi[a] = base[a * V_EBLK + V_COLS];
+  }
+  b2::cplx_dft16(yr, yi, Xr, Xi);
+  float2* dst = p_col + k2 * (16 * V_COLS);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) dst[k1 * V_COLS] = b2::vfma(Xr[k1], Xr[k1], b2::vmul(Xi[k1], Xi[k1]));
+}
+
+__device__ __forceinline__ void v_pass2_real(const float2* __restrict__ e_col, float2* __restrict__ p_col) {
+  float2 y[16], P[9];
+#pragma unroll
+  for (int a = 0; a < 16; ++a) y[a] = e_col[a * V_EBLK];
+  b2::real_dft16_power(y, P);
+#pragma unroll
+  for (int k1 = 0; k1 < 9; ++k1) p_col[k1 * V_COLS] = P[k1];
+}
+
+// mel, one frame per lane (scalar): p_lane points at this lane's float inside row 0 of P, rows are 32 floats apart
+template <int J, int LEN, int OFF, int REL, int NB>
+__device__ __forceinline__ void v_mel_taps(const float (&pb)[NB], float& acc) {
+  if constexpr (J < LEN) {
+    constexpr float wt = w_mel_wt(OFF + J);
+    acc = (J == 0) ? pb[REL + J] * wt : __fmaf_rn(pb[REL + J], wt, acc);
+    v_mel_taps<J + 1, LEN, OFF, REL, NB>(pb, acc);
+  }
+}
+
+template <int M, int FE, int BLO, int NB>
+__device__ __forceinline__ void v_mel_filters(const float (&pb)[NB], float* __restrict__ out_col, bool valid, float& emax) {
+  if constexpr (M < FE) {
+    float acc;
+    v_mel_taps<0, w_mel_len(M), w_mel_off(M), w_mel_start(M) - BLO, NB>(pb, acc);
+    const float e = fmaxf(acc, 1e-10f);
+    emax = fmaxf(emax, valid ? e : 0.0f);
+    const float y = w_norm_log(e);
+    if (valid) out_col[(size_t)M * W_NFRAME] = y;
+    v_mel_filters<M + 1, FE, BLO, NB>(pb, out_col, valid, emax);
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void v_mel_share(const float* __restrict__ p_lane, float* __restrict__ out_col, bool valid, float& emax) {
+  constexpr int FB = w_mel_first(S), FE = w_mel_first(S + 1);
+  constexpr int BLO = w_mel_start(FB), BHI = w_mel_start(FE - 1) + w_mel_len(FE - 1);
+  constexpr int NB = BHI - BLO;
+  float pb[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) pb[k] = p_lane[w_bin_row(BLO + k) * (2 * V_COLS)];
+  v_mel_filters<FB, FE, BLO, NB>(pb, out_col, valid, emax);
+}
+
+__device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0, const float2* __restrict__ s_p,
+                                            float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
+  // lane l < 16: first frame of column l; lane l >= 16: second frame (8 frames later) of column l - 16
+  const int col = lane & 15, half = lane >> 4;
+  const int frame = f0 + 16 * (col >> 3) + (col & 7) + 8 * half;
+  const bool valid = frame < W_NFRAME;
+  const float* pl = reinterpret_cast<const float*>(s_p) + 2 * col + half;
+  float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame;
+  float emax = 0.0f;
+#define V_MEL_CASE(w) case w: v_mel_share<2 * w>(pl, out_col, valid, emax); v_mel_share<2 * w + 1>(pl, out_col, valid, emax); break;
+  switch (warp) { V_MEL_CASE(0) V_MEL_CASE(1) V_MEL_CASE(2) V_MEL_CASE(3) V_MEL_CASE(4) V_MEL_CASE(5) V_MEL_CASE(6) default: V_MEL_CASE(7) }
+#undef V_MEL_CASE
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  if (lane == 0 && emax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(emax));
+}
+
+#ifndef V_ROTATE
+#define V_ROTATE 1
+#endif
+#ifndef V_MEL_FIRST
+#define V_MEL_FIRST(w) (((w) >> 2) & 1)
+#endif
+
+__global__ void __launch_bounds__(V_THREADS, 2)
+whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
+                        const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
+                        int batch, float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
+  extern __shared__ __align__(1024) float smem[];
+  float* s_audio = smem;
+  float2* s_e = reinterpret_cast<float2*>(smem + V_SM_AUDIO);
+  float2* s_p = reinterpret_cast<float2*>(smem + V_SM_AUDIO + V_SM_E);
+  int* s_off = reinterpret_cast<int*>(smem + V_SM_AUDIO + V_SM_E + V_SM_P);
+  float* s_win = smem + V_SM_AUDIO + V_SM_E + V_SM_P + 16 * 28;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + V_SM_AUDIO + V_SM_E + V_SM_P + W_SM_TAB);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntiles = batch * V_TILES_PER_CLIP;
+  for (int i = tid; i < 16 * 28; i += V_THREADS) { s_off[i] = c_wp1_off[i]; s_win[i] = c_wp1_win[i]; }
+  if (tid == 0) { mbar_init(s_bar, 1); fence_proxy_async(); }
+  __syncthreads();
+
+  // pass-1 role: class a = 4 (warp & 3) + lane / 8, frame pair (16 fg + i, 16 fg + 8 + i) = column 8 fg + i, fg = warp >> 2
+  const int p1_a = 4 * (warp & 3) + (lane >> 3);
+  const float* audio_lane = s_audio + (16 * (warp >> 2) + (lane & 7)) * W_PITCH;
+  float2* p1_dst = s_e + p1_a * V_EBLK + 8 * (warp >> 2) + (lane & 7);
+  // pass-2 role: warps 0..5 take tasks k2 = 1 + 2 warp + lane / 16, warp 6 the real task k2 = 0 (lanes 0..15), warp 7 none
+  // The second CTA of an SM (CTAs are dealt round-robin, so blockIdx >= gridDim / 2) rotates the roles by two warps:
+  // the light pass-2 warps (real task, idle) then sit on the schedulers that carry two full tasks in the first CTA.
+  const int rot = (V_ROTATE && blockIdx.x >= (gridDim.x >> 1)) ? 2 : 0;
+  const int p2_warp = (warp + rot) & 7;
+  const int p2_col = lane & 15;
+  const int p2_k2 = 1 + 2 * p2_warp + (lane >> 4);
+  const bool mel_first = V_MEL_FIRST(warp);
+  constexpr int STAGE_TID = 7 * 32;
+
+  auto stage = [&](int t) -> bool {
+    const WTile wt = v_tile(wave, stride, lengths, t, use_tma);
+    if (wt.tma) {
+      if (tid == STAGE_TID) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(s_bar, V_TX_BYTES);
+        tma_load_3d(s_audio, &tmap, 120, wt.f0 - 2, wt.clip, s_bar);
+      }
+    } else {
+      v_stage_generic(wt, s_audio, warp, V_WARPS, lane);
+    }
+    return wt.tma;
+  };
+
+  int tile = blockIdx.x;
+  unsigned tma_parity = 0;
+  bool cur_tma = false;
+  if (tile < ntiles) cur_tma = stage(tile);
+  int prev_clip = -1, prev_f0 = 0;
+
+  for (;; tile += gridDim.x) {
+    const bool have = tile < ntiles;
+    if (have && cur_tma) { mbar_wait(s_bar, tma_parity); tma_parity ^= 1u; }
+    __syncthreads();                       // audio(tile) visible; P(previous tile) complete; E is free
+
+    // ---- phase A: mel(previous tile) + pass 1(this tile) ----------------------------------------------
+#pragma unroll 1
+    for (int step = 0; step < 2; ++step) {
+      if ((step == 0) == mel_first) {
+        if (prev_clip >= 0) v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, clip_max_bits);
+      } else if (have) {
+        v_pass1(p1_a, audio_lane, p1_dst, s_off, s_win);
+      }
+    }
+    if (!have) break;
+    __syncthreads();                       // E complete; the audio tile and P are dead from here on
+
+    // ---- phase B: TMA prefetch of the next tile + pass 2(this tile) -----------------------------------
+    {
+      const int next = tile + gridDim.x;
+      cur_tma = (next < ntiles) ? stage(next) : false;
+    }
+    if (p2_warp < 6) v_pass2(p2_k2, s_e + p2_col, s_p + p2_col);
+    else if (p2_warp == 6 && lane < 16) v_pass2_real(s_e + p2_col, s_p + p2_col);
+    prev_clip = tile / V_TILES_PER_CLIP;
+    prev_f0 = (tile - prev_clip * V_TILES_PER_CLIP) * V_TILE;
+  }
+}
+
