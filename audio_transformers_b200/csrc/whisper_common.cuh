@@ -79,6 +79,7 @@ struct WTile {
   int clip, f0;
   int L;                // valid samples (<= 480000)
   bool tma;             // interior tile: fetched by TMA; otherwise the generic path below
+  bool silent;          // every sample the tile touches lies in the zero padding past the clip (32-frame kernel only)
 };
 
 __device__ __forceinline__ WTile w_tile(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,

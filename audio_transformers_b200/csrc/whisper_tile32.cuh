@@ -32,9 +32,29 @@ __device__ __forceinline__ WTile v_tile(const float* __restrict__ wave, long lon
   const long long len_ll = lengths ? (long long)__ldg(lengths + t.clip) : stride;
   t.L = (int)(len_ll < 0 ? 0 : (len_ll > W_NSAMP ? W_NSAMP : len_ll));
   t.src = wave + (size_t)t.clip * (size_t)stride;
-  const long long g0 = (long long)t.f0 * W_HOP - W_NFFT / 2;
-  t.tma = use_tma && g0 >= 0 && g0 + V_ROWS * W_HOP <= t.L && g0 + V_ROWS * W_HOP + 4 <= stride;
+  const long long g0 = (long long)t.f0 * W_HOP - W_NFFT / 2, gend = g0 + V_ROWS * W_HOP;
+  t.tma = use_tma && g0 >= 0 && gend <= t.L && gend + 4 <= stride;
+  // Smallest clip index any row of the tile maps to (left reflection reaches index 0; right reflection maps
+  // g >= 480000 to 959998 - g).  If that is already past the clip, the tile sees only zero padding: its frames are
+  // exactly the floor value and neither the audio copy nor the FFT is needed.  Whisper inputs are mostly much
+  // shorter than the 30 s they are padded to, so for real batches this is the common tile.
+  long long jmin = g0 < 0 ? 0 : g0;
+  if (gend > W_NSAMP) { const long long r = 2LL * (W_NSAMP - 1) - (gend - 1); jmin = r < jmin ? r : jmin; }
+  t.silent = jmin >= t.L;
   return t;
+}
+
+// A tile of pure zero padding: mel = 0 -> max(., 1e-10) -> the same w_norm_log as the computed path (all 8 warps).
+__device__ __forceinline__ void v_write_silent(const WTile& t, int warp, int lane, float* __restrict__ out,
+                                               unsigned int* __restrict__ clip_max_bits) {
+  const int frame = t.f0 + lane;
+  const float y = w_norm_log(1e-10f);
+  if (frame < W_NFRAME) {
+    float* out_col = out + (size_t)t.clip * (W_NMEL * W_NFRAME) + frame;
+#pragma unroll 5
+    for (int m = warp; m < W_NMEL; m += V_WARPS) out_col[(size_t)m * W_NFRAME] = y;
+  }
+  if (warp == 0 && lane == 0) atomicMax(clip_max_bits + t.clip, __float_as_uint(1e-10f));
 }
 
 __device__ __forceinline__ void v_stage_generic(const WTile& t, float* __restrict__ s_audio, int part, int nparts, int lane) {
@@ -194,8 +214,17 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
   const bool mel_first = V_MEL_FIRST(warp);
   constexpr int STAGE_TID = 7 * 32;
 
-  auto stage = [&](int t) -> bool {
-    const WTile wt = v_tile(wave, stride, lengths, t, use_tma);
+  // first tile at or after `t` (stride gridDim) that needs computing; tiles of pure zero padding on the way are
+  // written out immediately, so the pipeline below only ever sees tiles with audio in them
+  auto next_tile = [&](int t, WTile& wt) -> int {
+    for (; t < ntiles; t += gridDim.x) {
+      wt = v_tile(wave, stride, lengths, t, use_tma);
+      if (!wt.silent) break;
+      v_write_silent(wt, warp, lane, out, clip_max_bits);
+    }
+    return t;
+  };
+  auto stage = [&](const WTile& wt) -> bool {
     if (wt.tma) {
       if (tid == STAGE_TID) {
         fence_proxy_async();
@@ -208,13 +237,14 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
     return wt.tma;
   };
 
-  int tile = blockIdx.x;
+  WTile wt;
+  int tile = next_tile(blockIdx.x, wt);
   unsigned tma_parity = 0;
   bool cur_tma = false;
-  if (tile < ntiles) cur_tma = stage(tile);
+  if (tile < ntiles) cur_tma = stage(wt);
   int prev_clip = -1, prev_f0 = 0;
 
-  for (;; tile += gridDim.x) {
+  for (;;) {
     const bool have = tile < ntiles;
     if (have && cur_tma) { mbar_wait(s_bar, tma_parity); tma_parity ^= 1u; }
     __syncthreads();                       // audio(tile) visible; P(previous tile) complete; E is free
@@ -232,14 +262,13 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
     __syncthreads();                       // E complete; the audio tile and P are dead from here on
 
     // ---- phase B: TMA prefetch of the next tile + pass 2(this tile) -----------------------------------
-    {
-      const int next = tile + gridDim.x;
-      cur_tma = (next < ntiles) ? stage(next) : false;
-    }
+    const int next = next_tile(tile + gridDim.x, wt);
+    cur_tma = (next < ntiles) ? stage(wt) : false;
     if (p2_warp < 6) v_pass2(p2_k2, s_e + p2_col, s_p + p2_col);
     else if (p2_warp == 6 && lane < 16) v_pass2_real(s_e + p2_col, s_p + p2_col);
     prev_clip = tile / V_TILES_PER_CLIP;
     prev_f0 = (tile - prev_clip * V_TILES_PER_CLIP) * V_TILE;
+    tile = next;
   }
 }
 
