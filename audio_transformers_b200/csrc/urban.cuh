@@ -13,7 +13,7 @@
 //   mel     64 HTK filters (998 taps), optional log(. + eps), coalesced stores
 // ------------------------------------------------------------------------------------------------
 constexpr int U_NFFT = 1024, U_HOP = 512, U_NMEL = 64, U_NBIN = 513;
-constexpr int U_TILE = 32, U_THREADS = 256, U_WARPS = U_THREADS / 32;
+constexpr int U_TILE = 32, U_THREADS = 512, U_WARPS = U_THREADS / 32;
 constexpr int U_SPAN = (U_TILE - 1) * U_HOP + U_NFFT;           // 16896 samples
 constexpr int U_PITCH = U_HOP + 1;                              // 513
 constexpr int U_ROWS = U_SPAN / U_HOP;                          // 33
