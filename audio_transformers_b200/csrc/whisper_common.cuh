@@ -73,6 +73,10 @@ __device__ __forceinline__ void tma_load_3d(float* smem_dst, const CUtensorMap* 
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* tmap, int x, int y, int z) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // ---- stage one tile of audio into shared memory ------------------------------------------------
 struct WTile {
   const float* src;     // clip base

@@ -175,6 +175,9 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
   if (lane == 0 && emax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(emax));
 }
 
+#ifndef V_L2_PREFETCH
+#define V_L2_PREFETCH 1
+#endif
 #ifndef V_ROTATE
 #define V_ROTATE 1
 #endif
@@ -248,6 +251,17 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
     const bool have = tile < ntiles;
     if (have && cur_tma) { mbar_wait(s_bar, tma_parity); tma_parity ^= 1u; }
     __syncthreads();                       // audio(tile) visible; P(previous tile) complete; E is free
+#if V_L2_PREFETCH
+    // The copy of the next tile can only be issued once pass 1 has released the audio buffer (phase B), which leaves
+    // it one phase to arrive; pulling its box into L2 a phase earlier takes the DRAM latency off that path.
+    if (tid == STAGE_TID && have) {
+      const int nx = tile + gridDim.x;
+      if (nx < ntiles) {
+        const WTile pt = v_tile(wave, stride, lengths, nx, use_tma);
+        if (pt.tma) tma_prefetch_l2_3d(&tmap, 120, pt.f0 - 2, pt.clip);
+      }
+    }
+#endif
 
     // ---- phase A: mel(previous tile) + pass 1(this tile) ----------------------------------------------
 #pragma unroll 1
