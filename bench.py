@@ -223,7 +223,6 @@ def run_ours(args) -> dict | None:
     for w in range(W):
         ops.whisper_logmel(dev_pool[w % N_POOL], None)
     barrier()
-    ops.profile_begin(dev, max_launches=min(K, 8192))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start = time.perf_counter()
     e0.record()
@@ -233,6 +232,13 @@ def run_ours(args) -> dict | None:
     barrier()
     t_end = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
+    # the dominant kernel alone, for the roofline: a second pass with the library's per-launch event pairs switched on
+    # (kept out of the timed loop above: the extra event records cost ~3 % of a 64-clip step)
+    Kp = min(K, 1000)
+    ops.profile_begin(dev, max_launches=Kp)
+    for k in range(Kp):
+        ops.whisper_logmel(dev_pool[k % N_POOL], None)
+    barrier()
     kern_ms, kern_n = ops.profile_end(dev)
     checksum = float(out[0, :, :8].sum().item())
 
@@ -297,7 +303,7 @@ def run_ours(args) -> dict | None:
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": args.traffic if args.traffic is not None else ncu_traffic(B),
-                     "kernel": "whisper_logmel_kernel", "kernel_ms": kern_ms_avg, "launches_timed": kern_n,
+                     "kernel": "whisper_logmel_kernel32", "kernel_ms": kern_ms_avg, "launches_timed": kern_n,
                      "bytes_per_launch": BYTES_PER_CLIP * B, "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 480000 * 4,
                 "d2h_bytes_per_step": B * 80 * 3000 * 4,
