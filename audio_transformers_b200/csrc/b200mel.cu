@@ -162,7 +162,8 @@ int b200mel_profile_end(b200mel_handle* h, double* total_ms, int32_t* launches) 
 size_t b200mel_workspace_bytes(const b200mel_handle* h, int32_t batch) {
   if (!h || batch <= 0) return 0;
   if (h->preset != B200MEL_PRESET_WHISPER) return 0;
-  return ((size_t)batch * sizeof(unsigned int) + 255) & ~(size_t)255;
+  // 32-frame kernel: one float per (clip, tile, warp); 64-frame kernel: one word per clip
+  return ((size_t)batch * V_SLOTS_PER_CLIP * sizeof(float) + 255) & ~(size_t)255;
 }
 
 int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples,
@@ -179,9 +180,13 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
     return fail(B200MEL_ERR_WORKSPACE, "whisper_logmel: workspace too small (see b200mel_workspace_bytes)");
   if ((long long)batch * V_TILES_PER_CLIP > 0x7fffffffLL) return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel: batch too large for one launch");
   cudaStream_t stream = (cudaStream_t)stream_;
+  const bool k32 = getenv("B200MEL_KERNEL64") == nullptr;        // default: 32-frame tiles, two CTAs per SM
   unsigned int* clip_max = (unsigned int*)workspace;
-  cudaError_t e = cudaMemsetAsync(clip_max, 0, (size_t)batch * sizeof(unsigned int), stream);
-  if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
+  cudaError_t e = cudaSuccess;
+  if (!k32) {
+    e = cudaMemsetAsync(clip_max, 0, (size_t)batch * sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
+  }
   // TMA view of the audio: [clip][y][x], element (x, y, clip) = wave[clip * stride + 160 y + x], x < 284.  Rows
   // overlap (y-stride 160 samples < 284), which is what lets a box start at any sample with 16-byte aligned
   // strides.  NY is chosen so that every in-bounds element lies inside its clip's row of the buffer.
@@ -191,7 +196,6 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   if (stride_samples >= W_TMAP_X) {
     const cuuint64_t dims[3] = {(cuuint64_t)W_TMAP_X, (cuuint64_t)((stride_samples - W_TMAP_X) / W_HOP + 1), (cuuint64_t)batch};
     const cuuint64_t strides[2] = {(cuuint64_t)W_HOP * sizeof(float), (cuuint64_t)stride_samples * sizeof(float)};
-    const bool k32 = getenv("B200MEL_KERNEL64") == nullptr;
     const cuuint32_t box[3] = {(cuuint32_t)W_PITCH, (cuuint32_t)(k32 ? V_ROWS : W_ROWS), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = h->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)wave, dims, strides, box, estr,
@@ -204,11 +208,25 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   const int grid_main = ntiles < h->sm_count ? ntiles : h->sm_count;   // persistent: one 512-thread CTA per SM
   const bool prof = h->prof_on && h->prof_n < h->prof_cap;
   if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
-  if (getenv("B200MEL_KERNEL64") == nullptr) {     // default: 32-frame tiles, two CTAs per SM
+  if (k32) {
     const long long nt = (long long)batch * V_TILES_PER_CLIP;
     const int grid32 = nt < 2LL * h->sm_count ? (int)nt : 2 * h->sm_count;
-    whisper_logmel_kernel32<<<grid32, V_THREADS, V_SMEM_BYTES, stream>>>(
-        tmap, use_tma, wave, (long long)stride_samples, lengths, batch, out, clip_max);
+    // programmatic stream serialisation: the kernel may begin while the previous kernel of the stream is finishing
+    // (it waits with griddepcontrol.wait before its first global write); with profiling on the event records sit
+    // between the kernels and switch the overlap off
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid32);
+    cfg.blockDim = dim3(V_THREADS);
+    cfg.dynamicSmemBytes = V_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, whisper_logmel_kernel32, tmap, use_tma, wave, (long long)stride_samples, lengths, (int)batch, out,
+                           (float*)workspace);
+    if (e != cudaSuccess) return fail_cuda(e, "whisper_logmel_kernel32 launch");
   } else {
     whisper_logmel_kernel<<<grid_main, W_THREADS, W_SMEM_BYTES, stream>>>(
         tmap, use_tma, wave, (long long)stride_samples, lengths, batch, out, clip_max);
@@ -216,8 +234,14 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "whisper_logmel_kernel launch");
-  dim3 grid(30, batch);
-  whisper_clamp_kernel<<<grid, 256, 0, stream>>>(out, clip_max, batch);
+  if (k32) {
+    const int items = batch * CL_PARTS;
+    const int grid = items < CL_CTAS_PER_SM * h->sm_count ? items : CL_CTAS_PER_SM * h->sm_count;
+    whisper_clamp_kernel32<<<grid, CL_THREADS, 0, stream>>>(out, (const float*)workspace, batch);
+  } else {
+    dim3 grid(30, batch);
+    whisper_clamp_kernel<<<grid, 256, 0, stream>>>(out, clip_max, batch);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "whisper_clamp_kernel launch");
   return B200MEL_OK;

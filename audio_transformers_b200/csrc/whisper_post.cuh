@@ -16,6 +16,48 @@ whisper_clamp_kernel(float* __restrict__ out, const unsigned int* __restrict__ c
   }
 }
 
+// The same pass for the 32-frame kernel: the clip maximum is the maximum over the clip's (tile, warp) slots.
+// A few resident CTAs per SM loop over (clip, tenth of a clip) work items, so that the whole grid is running from the
+// first instant and `launch_dependents` lets the NEXT call's log-mel kernel start underneath this pass.
+#ifndef CL_CTAS_PER_SM
+#define CL_CTAS_PER_SM 4
+#endif
+constexpr int CL_THREADS = 256, CL_PARTS = 10;
+__global__ void __launch_bounds__(CL_THREADS, 8)
+whisper_clamp_kernel32(float* __restrict__ out, const float* __restrict__ tile_max, int batch) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  __shared__ float s_red[CL_THREADS / 32];
+  constexpr int VEC_PER_PART = W_NMEL * W_NFRAME / 4 / CL_PARTS;       // 6000
+  const int tid = threadIdx.x;
+  for (int item = blockIdx.x; item < batch * CL_PARTS; item += gridDim.x) {
+    const int clip = item / CL_PARTS, part = item - clip * CL_PARTS;
+    float m = 0.0f;
+    for (int i = tid; i < V_SLOTS_PER_CLIP; i += CL_THREADS) m = fmaxf(m, __ldcg(tile_max + (size_t)clip * V_SLOTS_PER_CLIP + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();                                   // s_red of the previous item has been read
+    if ((tid & 31) == 0) s_red[tid >> 5] = m;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < CL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+    const float thr = w_norm_log(m) - 2.0f;
+    float4* p = reinterpret_cast<float4*>(out + (size_t)clip * (W_NMEL * W_NFRAME)) + part * VEC_PER_PART;
+    for (int i0 = tid; i0 < VEC_PER_PART; i0 += 4 * CL_THREADS) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (i0 + j * CL_THREADS < VEC_PER_PART) v[j] = p[i0 + j * CL_THREADS];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * CL_THREADS;
+        if (i < VEC_PER_PART && (v[j].x < thr || v[j].y < thr || v[j].z < thr || v[j].w < thr)) {
+          v[j].x = fmaxf(v[j].x, thr); v[j].y = fmaxf(v[j].y, thr); v[j].z = fmaxf(v[j].z, thr); v[j].w = fmaxf(v[j].w, thr);
+          p[i] = v[j];
+        }
+      }
+    }
+  }
+}
+
 __global__ void whisper_frame_mask_kernel(const int* __restrict__ lengths, int batch, int* __restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * W_NFRAME) return;

@@ -44,9 +44,17 @@ __device__ __forceinline__ WTile v_tile(const float* __restrict__ wave, long lon
   return t;
 }
 
+// Workspace of this kernel: one float per (clip, tile, warp) = the largest mel energy that warp saw in that tile.
+// Every slot is written exactly once per launch, so the workspace needs no zeroing (no memset node, no atomics),
+// and the clip-floor pass reduces a clip's 94 x 8 slots itself.
+constexpr int V_SLOTS_PER_CLIP = V_TILES_PER_CLIP * V_WARPS;
+__device__ __forceinline__ float* v_slot(float* __restrict__ tile_max, int clip, int f0, int warp) {
+  return tile_max + (size_t)clip * V_SLOTS_PER_CLIP + (f0 / V_TILE) * V_WARPS + warp;
+}
+
 // A tile of pure zero padding: mel = 0 -> max(., 1e-10) -> the same w_norm_log as the computed path (all 8 warps).
 __device__ __forceinline__ void v_write_silent(const WTile& t, int warp, int lane, float* __restrict__ out,
-                                               unsigned int* __restrict__ clip_max_bits) {
+                                               float* __restrict__ tile_max) {
   const int frame = t.f0 + lane;
   const float y = w_norm_log(1e-10f);
   if (frame < W_NFRAME) {
@@ -54,7 +62,7 @@ __device__ __forceinline__ void v_write_silent(const WTile& t, int warp, int lan
 #pragma unroll 5
     for (int m = warp; m < W_NMEL; m += V_WARPS) out_col[(size_t)m * W_NFRAME] = y;
   }
-  if (warp == 0 && lane == 0) atomicMax(clip_max_bits + t.clip, __float_as_uint(1e-10f));
+  if (lane == 0) *v_slot(tile_max, t.clip, t.f0, warp) = 1e-10f;
 }
 
 __device__ __forceinline__ void v_stage_generic(const WTile& t, float* __restrict__ s_audio, int part, int nparts, int lane) {
@@ -159,7 +167,7 @@ __device__ __forceinline__ void v_mel_share(const float* __restrict__ p_lane, fl
 }
 
 __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0, const float2* __restrict__ s_p,
-                                            float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
+                                            float* __restrict__ out, float* __restrict__ tile_max) {
   // lane l < 16: first frame of column l; lane l >= 16: second frame (8 frames later) of column l - 16
   const int col = lane & 15, half = lane >> 4;
   const int frame = f0 + 16 * (col >> 3) + (col & 7) + 8 * half;
@@ -172,7 +180,7 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
 #undef V_MEL_CASE
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
-  if (lane == 0 && emax > 0.0f) atomicMax(clip_max_bits + clip, __float_as_uint(emax));
+  if (lane == 0) *v_slot(tile_max, clip, f0, warp) = emax;
 }
 
 #ifndef V_L2_PREFETCH
@@ -188,7 +196,7 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
 __global__ void __launch_bounds__(V_THREADS, 2)
 whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
                         const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
-                        int batch, float* __restrict__ out, unsigned int* __restrict__ clip_max_bits) {
+                        int batch, float* __restrict__ out, float* __restrict__ tile_max) {
   extern __shared__ __align__(1024) float smem[];
   float* s_audio = smem;
   float2* s_e = reinterpret_cast<float2*>(smem + V_SM_AUDIO);
@@ -217,13 +225,19 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
   const bool mel_first = V_MEL_FIRST(warp);
   constexpr int STAGE_TID = 7 * 32;
 
+  // The kernel is launched with programmatic stream serialisation: it may start while the previous kernel of the
+  // stream (normally the clip-floor pass of the previous call) is still running.  Everything up to here and the
+  // first tile's copy and two DFT passes only READ the audio; the first global WRITE waits for the dependency.
+  bool dep_ok = false;
+  auto dep_wait = [&]() { if (!dep_ok) { asm volatile("griddepcontrol.wait;" ::: "memory"); dep_ok = true; } };
   // first tile at or after `t` (stride gridDim) that needs computing; tiles of pure zero padding on the way are
   // written out immediately, so the pipeline below only ever sees tiles with audio in them
   auto next_tile = [&](int t, WTile& wt) -> int {
     for (; t < ntiles; t += gridDim.x) {
       wt = v_tile(wave, stride, lengths, t, use_tma);
       if (!wt.silent) break;
-      v_write_silent(wt, warp, lane, out, clip_max_bits);
+      dep_wait();
+      v_write_silent(wt, warp, lane, out, tile_max);
     }
     return t;
   };
@@ -267,7 +281,7 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
 #pragma unroll 1
     for (int step = 0; step < 2; ++step) {
       if ((step == 0) == mel_first) {
-        if (prev_clip >= 0) v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, clip_max_bits);
+        if (prev_clip >= 0) { dep_wait(); v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, tile_max); }
       } else if (have) {
         v_pass1(p1_a, audio_lane, p1_dst, s_off, s_win);
       }

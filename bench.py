@@ -299,7 +299,7 @@ def run_ours(args) -> dict | None:
                    "l2": f"inputs rotate over {N_POOL} distinct {B * 1.92:.0f} MB batches (> 126 MB L2)",
                    "timing": "CUDA events on the launch stream, max over ranks",
                    "e2e_steps": Ke, "e2e_wall_s": round(e2e_wall, 4), "checksum": checksum,
-                   "gpu_launches_scope": "per rank and step: fused log-mel kernel (TMA-fed) + clip-floor pass; plus one 256-byte memset node"},
+                   "gpu_launches_scope": "per rank and step: fused log-mel kernel (TMA-fed) + clip-floor pass; no memset"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": args.traffic if args.traffic is not None else ncu_traffic(B),
