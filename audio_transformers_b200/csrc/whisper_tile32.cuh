@@ -225,18 +225,17 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
   const bool mel_first = V_MEL_FIRST(warp);
   constexpr int STAGE_TID = 7 * 32;
 
-  // The kernel is launched with programmatic stream serialisation: it may start while the previous kernel of the
-  // stream (normally the clip-floor pass of the previous call) is still running.  Everything up to here and the
-  // first tile's copy and two DFT passes only READ the audio; the first global WRITE waits for the dependency.
-  bool dep_ok = false;
-  auto dep_wait = [&]() { if (!dep_ok) { asm volatile("griddepcontrol.wait;" ::: "memory"); dep_ok = true; } };
+  // The kernel is launched with programmatic stream serialisation: it may become resident and run its prologue
+  // (tables, mbarrier, role set-up: nothing that touches global memory) while the previous kernel of the stream -- the
+  // clip-floor pass of the previous call, or whatever produced the audio -- is still finishing.  Everything after this
+  // wait sees that kernel's results; nothing before it reads or writes global memory.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // first tile at or after `t` (stride gridDim) that needs computing; tiles of pure zero padding on the way are
   // written out immediately, so the pipeline below only ever sees tiles with audio in them
   auto next_tile = [&](int t, WTile& wt) -> int {
     for (; t < ntiles; t += gridDim.x) {
       wt = v_tile(wave, stride, lengths, t, use_tma);
       if (!wt.silent) break;
-      dep_wait();
       v_write_silent(wt, warp, lane, out, tile_max);
     }
     return t;
@@ -281,7 +280,7 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
 #pragma unroll 1
     for (int step = 0; step < 2; ++step) {
       if ((step == 0) == mel_first) {
-        if (prev_clip >= 0) { dep_wait(); v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, tile_max); }
+        if (prev_clip >= 0) v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, tile_max);
       } else if (have) {
         v_pass1(p1_a, audio_lane, p1_dst, s_off, s_win);
       }
