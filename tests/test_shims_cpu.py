@@ -79,3 +79,24 @@ def test_urban_module_buffers():
     sd = m.state_dict()
     assert sd["spectrogram.window"].shape == (1024,) and sd["mel_scale.fb"].shape == (513, 64)
     assert (m.n_fft, m.hop_length, m.n_mels, m.sample_rate) == (1024, 512, 64, 22050)
+
+
+def test_urban_front_end_host_side():
+    """B200UrbanFrontEnd mirrors UrbanSoundDataset's constructor defaults (REF:urban_sounds/dataset.py:8-24); the tap
+    table has torchaudio's shape; segment mode validates its arguments before touching the device."""
+    from audio_transformers_b200.urban import B200UrbanFrontEnd, sinc_resample_kernel
+    k, width, orig, new = sinc_resample_kernel(44100, 22050)
+    assert (orig, new, width) == (2, 1, 13) and k.shape == (1, 28) and k.dtype == np.float32      # SURVEY.md section 8f-2
+    assert abs(float(k.sum()) - 1.0) < 2e-3                                                         # unit DC gain
+    k, width, orig, new = sinc_resample_kernel(48000, 22050)
+    assert (orig, new) == (320, 147) and k.shape == (147, 2 * width + 320)
+    if not torch.cuda.is_available():
+        fe = B200UrbanFrontEnd(device="cpu")
+        assert fe.target_length == 88200
+        with pytest.raises(RuntimeError):
+            fe.process_audio(np.zeros(1000), 44100)
+    ext = B200WhisperFeatureExtractor()
+    with pytest.raises(ValueError):
+        ext.segment_features(np.zeros(10, np.float32), 80001)
+    with pytest.raises(ValueError):
+        ext.segment_features(np.zeros(10, np.float32), 80000, sampling_rate=8000)
