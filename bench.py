@@ -326,18 +326,29 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch, if known (else null)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library prints meanwhile (e.g. NCCL's version banner, which
+    # goes to the C stdout) is routed to stderr by pointing fd 1 at fd 2 until the result is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 20
         args.warmup = args.warmup if args.warmup is not None else 3
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        print(json.dumps(run_reference(args)), flush=True)
+        emit(run_reference(args))
         return
     args.steps = args.steps if args.steps is not None else 2000
     args.warmup = max(args.warmup if args.warmup is not None else 20, 3)
     res = run_ours(args)
     if res is not None:
-        print(json.dumps(res), flush=True)
+        emit(res)
 
 
 if __name__ == "__main__":
