@@ -201,13 +201,13 @@ B2_CX int w_bin_row(int k) {
 }
 constexpr int W_MEL_FIXED_COST = 8;
 B2_CX int w_mel_total_cost() { int c = 0; for (int m = 0; m < 80; ++m) c += w_mel_len(m) + W_MEL_FIXED_COST; return c; }
-// first filter of warp w (w = 16 -> 80): the cumulative cost is cut into 16 equal shares
-B2_CX int w_mel_first(int w) {
-  if (w >= 16) return 80;
+// first filter of share w out of ns (w = ns -> 80): the cumulative cost is cut into ns equal shares
+B2_CX int w_mel_first(int w, int ns = 16) {
+  if (w >= ns) return 80;
   const int total = w_mel_total_cost();
   int c = 0;
   for (int m = 0; m < 80; ++m) {
-    if (c * 16 >= w * total) return m;
+    if (c * ns >= w * total) return m;
     c += w_mel_len(m) + W_MEL_FIXED_COST;
   }
   return 80;
