@@ -172,6 +172,27 @@ def test_tma_and_generic_staging_agree(ops, stride, monkeypatch):
     assert np.abs(a - ref).max() <= TOL
 
 
+def test_cuda_graph_capture_and_replay(ops):
+    """include/b200mel.h promises stream-ordered, allocation-free, sync-free calls: a call (TMA descriptor as a kernel
+    parameter, programmatic launch attribute and all) can be captured once and replayed on new audio."""
+    clips = signals.whisper_batch(4, seed=17)
+    static_in = torch.from_numpy(clips).cuda()
+    ops.whisper_logmel(static_in, None)                      # warm-up outside capture (handle creation)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        static_out = ops.whisper_logmel(static_in, None)
+    other = signals.whisper_batch(4, seed=18)
+    static_in.copy_(torch.from_numpy(other))
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.abs(static_out.cpu().numpy() - O.whisper_logmel(list(other))).max() <= TOL
+    static_in.copy_(torch.from_numpy(clips))
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.abs(static_out.cpu().numpy() - O.whisper_logmel(list(clips))).max() <= TOL
+
+
 def test_frame_mask(ops):
     lens = torch.tensor([1, 160, 161, 480000, 600000], dtype=torch.int32).cuda()
     m = ops.whisper_frame_mask(lens).cpu().numpy()
