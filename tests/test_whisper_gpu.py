@@ -193,6 +193,23 @@ def test_cuda_graph_capture_and_replay(ops):
     assert np.abs(static_out.cpu().numpy() - O.whisper_logmel(list(clips))).max() <= TOL
 
 
+def test_large_ragged_batch(ops):
+    """Many more tiles than resident CTAs, random lengths (tiles of pure padding are skipped, edge tiles use the
+    store path, interior tiles TMA): spot-check clips against the oracle."""
+    B = 400
+    rng = np.random.default_rng(5)
+    base = signals.whisper_batch(12, seed=9)
+    idx = rng.integers(0, 12, size=B)
+    lens = rng.integers(1, 480001, size=B).astype(np.int32)
+    lens[::7] = 480000
+    wave = torch.from_numpy(base).cuda()[torch.from_numpy(idx).cuda()].contiguous()
+    out = ops.whisper_logmel(wave, torch.from_numpy(lens).cuda())
+    assert bool(torch.isfinite(out).all())
+    for b in (0, 1, 7, 233, B - 1, int(np.argmin(lens)), int(np.argmax(lens))):
+        ref = O.whisper_logmel([base[idx[b]][:lens[b]]])[0]
+        assert np.abs(out[b].cpu().numpy() - ref).max() <= TOL, b
+
+
 def test_frame_mask(ops):
     lens = torch.tensor([1, 160, 161, 480000, 600000], dtype=torch.int32).cuda()
     m = ops.whisper_frame_mask(lens).cpu().numpy()
