@@ -16,6 +16,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+#include <vector>
+
 #include "../../include/b200mel.h"
 
 #define B200MEL_CONST __constant__
@@ -326,6 +329,53 @@ int b200mel_debug_set_trace(void* dev_ptr) {
   return cudaMemcpyToSymbol(g_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
 }
 #endif
+
+// Host-side staging helper: ragged clips (float32 or float64, one pointer per clip) -> one row-major float32 buffer
+// (pinned, ideally) with `dst_stride` floats per row, converting and copying with `threads` host threads.  Only
+// min(len, max_samples) samples of a clip are copied; the tail of a row is left untouched (the kernels never read it).
+int b200mel_host_pack(const void* const* clips, const int64_t* lengths, int32_t n, int32_t src_is_f64,
+                      int64_t max_samples, float* dst, int64_t dst_stride, int32_t* out_lengths, int32_t threads) {
+  if (n < 0 || (n > 0 && (!clips || !lengths || !dst))) return fail(B200MEL_ERR_BAD_ARG, "host_pack: NULL argument");
+  if (dst_stride <= 0 || max_samples < 0) return fail(B200MEL_ERR_BAD_ARG, "host_pack: bad stride / max_samples");
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    int64_t L = lengths[i] < 0 ? 0 : (lengths[i] > max_samples ? max_samples : lengths[i]);
+    if (L > dst_stride) return fail(B200MEL_ERR_BAD_ARG, "host_pack: a clip is longer than dst_stride");
+    if (L > 0 && !clips[i]) return fail(B200MEL_ERR_BAD_ARG, "host_pack: NULL clip pointer");
+    if (out_lengths) out_lengths[i] = (int32_t)L;
+    total += L;
+  }
+  if (total == 0) return B200MEL_OK;
+  // work is cut into equal sample ranges over the concatenation of all clips, so one long clip is shared by threads
+  int nt = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+  const int64_t min_chunk = 1 << 16;
+  if ((int64_t)nt > (total + min_chunk - 1) / min_chunk) nt = (int)((total + min_chunk - 1) / min_chunk);
+  auto work = [&](int64_t begin, int64_t end) {
+    int64_t pos = 0;
+    for (int i = 0; i < n && pos < end; ++i) {
+      const int64_t L = lengths[i] < 0 ? 0 : (lengths[i] > max_samples ? max_samples : lengths[i]);
+      const int64_t lo = begin > pos ? begin - pos : 0, hi = (end - pos) < L ? (end - pos) : L;
+      if (lo < hi) {
+        float* d = dst + (size_t)i * (size_t)dst_stride;
+        if (src_is_f64) {
+          const double* s = (const double*)clips[i];
+          for (int64_t k = lo; k < hi; ++k) d[k] = (float)s[k];
+        } else {
+          memcpy(d + lo, (const float*)clips[i] + lo, (size_t)(hi - lo) * sizeof(float));
+        }
+      }
+      pos += L;
+    }
+  };
+  if (nt <= 1) { work(0, total); return B200MEL_OK; }
+  std::vector<std::thread> pool;
+  pool.reserve(nt - 1);
+  const int64_t per = (total + nt - 1) / nt;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work, per * t, per * (t + 1) < total ? per * (t + 1) : total);
+  work(0, per < total ? per : total);
+  for (auto& th : pool) th.join();
+  return B200MEL_OK;
+}
 
 int64_t b200mel_get_table(int preset, int table, float* dst, int64_t capacity) {
   if (!dst) return fail(B200MEL_ERR_BAD_ARG, "get_table: dst is NULL");

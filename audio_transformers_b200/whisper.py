@@ -15,13 +15,16 @@ There is no CPU fallback: without a CUDA device (or without the built library) a
 """
 from __future__ import annotations
 
+import ctypes
 import logging
+import os
 from typing import Any, Optional, Sequence, Union
 
 import numpy as np
 import torch
 
 from . import ops
+from . import _lib
 from ._lib import PRESET_WHISPER, TABLE_FILTERBANK, get_table
 
 logger = logging.getLogger(__name__)
@@ -83,6 +86,10 @@ class B200WhisperFeatureExtractor:
         self.nb_max_frames = self.n_samples // hop_length
         self.device = torch.device(device) if device is not None else None
         self._mel_filters = None
+        # two pinned staging buffers used in turn, so that packing batch k+1 overlaps the H2D copy of batch k
+        self._stage = [None, None]
+        self._stage_turn = 0
+        self._pack_threads = max(1, min(16, os.cpu_count() or 1))
 
     # -- attributes the reference's notebook prints (experiments.ipynb:558-573) --------------------
     @property
@@ -119,17 +126,25 @@ class B200WhisperFeatureExtractor:
 
     @staticmethod
     def _canonicalise(raw_speech) -> list:
-        """HF:models/whisper/feature_extraction_whisper.py:274-292: always a batch, float32, mono."""
+        """HF:models/whisper/feature_extraction_whisper.py:274-292: always a batch, mono.  float32 / float64 arrays are
+        kept as they are (the float64 -> float32 cast of :285-286 happens inside the native packer, in parallel);
+        anything else is converted to float32 here."""
         is_batched_numpy = isinstance(raw_speech, np.ndarray) and raw_speech.ndim > 1
         if is_batched_numpy and raw_speech.ndim > 2:
             raise ValueError(f"Only mono-channel audio is supported for input to {_CLASS_NAME}")
         is_batched = is_batched_numpy or (
             isinstance(raw_speech, (list, tuple)) and len(raw_speech) > 0
             and isinstance(raw_speech[0], (np.ndarray, tuple, list, torch.Tensor)))
-        if is_batched:
-            clips = [np.asarray(c.detach().cpu() if isinstance(c, torch.Tensor) else c, dtype=np.float32) for c in raw_speech]
-        else:
-            clips = [np.asarray(raw_speech, dtype=np.float32)]
+
+        def one(c):
+            if isinstance(c, torch.Tensor):
+                c = c.detach().cpu().numpy()
+            c = np.asarray(c)
+            if c.dtype not in (np.float32, np.float64):
+                c = c.astype(np.float32)
+            return np.ascontiguousarray(c)
+
+        clips = [one(c) for c in raw_speech] if is_batched else [one(raw_speech)]
         for c in clips:
             if c.ndim != 1:
                 raise ValueError(f"Only mono-channel audio is supported for input to {_CLASS_NAME}")
@@ -137,17 +152,48 @@ class B200WhisperFeatureExtractor:
 
     def stage_host_batch(self, clips: Sequence[np.ndarray], dev: torch.device, max_length: int):
         """Ragged host clips -> one pinned (B, T4) staging buffer + int32 lengths, one H2D each.
-        Only ``min(len, max_length)`` samples per clip cross PCIe; padding is never materialised."""
-        lens = np.fromiter((min(len(c), max_length) for c in clips), dtype=np.int32, count=len(clips))
-        width = max(int(lens.max()) if len(lens) else 0, 4)
+        Only ``min(len, max_length)`` samples per clip cross PCIe; padding is never materialised.  The pack (and the
+        float64 -> float32 cast) is done by ``b200mel_host_pack`` on several host threads into one of two cached pinned
+        buffers; the previous copy out of that buffer is awaited first."""
+        n = len(clips)
+        lens64 = np.fromiter((len(c) for c in clips), dtype=np.int64, count=n)
+        width = max(int(np.minimum(lens64, max_length).max()) if n else 0, 4)
         width = (width + 3) // 4 * 4
-        host = torch.empty((len(clips), width), dtype=torch.float32, pin_memory=True)
-        hnp = host.numpy()
-        for i, c in enumerate(clips):
-            n = int(lens[i])
-            hnp[i, :n] = c[:n]
+        turn = self._stage_turn
+        self._stage_turn ^= 1
+        slot = self._stage[turn]
+        if slot is None or slot["host"].numel() < n * width or slot["lens"].numel() < n:
+            slot = {"host": torch.empty((max(n * width, 1),), dtype=torch.float32, pin_memory=True),
+                    "lens": torch.empty((max(n, 64),), dtype=torch.int32, pin_memory=True), "event": None}
+            self._stage[turn] = slot
+        elif slot["event"] is not None:
+            slot["event"].synchronize()
+        host = slot["host"][: n * width].view(n, width)
+        lens32 = slot["lens"][:n]
+        lib = _lib.load()
+        for is_f64, dt in ((1, np.float64), (0, np.float32)):
+            idx = [i for i, c in enumerate(clips) if c.dtype == dt]
+            if not idx:
+                continue
+            # rows of one dtype are packed together; the packer writes row j of the pointer list to dst row j, so it
+            # is handed the sub-batch through per-row destination pointers by calling it once per contiguous run
+            run_start = 0
+            while run_start < len(idx):
+                run_end = run_start
+                while run_end + 1 < len(idx) and idx[run_end + 1] == idx[run_end] + 1:
+                    run_end += 1
+                i0, cnt = idx[run_start], run_end - run_start + 1
+                ptrs = (ctypes.c_void_p * cnt)(*[clips[i0 + j].ctypes.data for j in range(cnt)])
+                st = lib.b200mel_host_pack(ptrs, lens64[i0:i0 + cnt].ctypes.data_as(ctypes.c_void_p), cnt, is_f64, max_length,
+                                           ctypes.c_void_p(host[i0].data_ptr()), width,
+                                           ctypes.c_void_p(lens32[i0:].data_ptr()), self._pack_threads)
+                _lib.check(st, "b200mel_host_pack")
+                run_start = run_end + 1
         wave = host.to(dev, non_blocking=True)
-        lengths = torch.from_numpy(lens).pin_memory().to(dev, non_blocking=True)
+        lengths = lens32.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        slot["event"] = ev
         return wave, lengths, host
 
     # -- the call -----------------------------------------------------------------------------------

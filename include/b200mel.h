@@ -126,6 +126,15 @@ int b200mel_urban_prep_f32(b200mel_handle* h, const float* audio, int64_t in_str
                            const float* taps, int32_t width, float* out, int64_t out_stride, int32_t out_samples,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host-side staging for the drop-in call shapes (REF:whisper_finetune/dataset.py:57-62 hands the extractor float64
+ * numpy arrays; HF converts them to float32 and pads on the host, feature_extraction_whisper.py:281-292).  Packs n
+ * ragged HOST clips (float32, or float64 when src_is_f64 != 0) into one row-major float32 HOST buffer `dst`
+ * (`dst_stride` floats per row; pinned memory makes the following H2D copy asynchronous), converting and copying with
+ * up to `threads` host threads.  Only min(lengths[i], max_samples) samples of a clip are copied; out_lengths (may be
+ * NULL) receives those counts.  No CUDA calls. */
+int b200mel_host_pack(const void* const* clips, const int64_t* lengths, int32_t n, int32_t src_is_f64,
+                      int64_t max_samples, float* dst, int64_t dst_stride, int32_t* out_lengths, int32_t threads);
+
 /* Optional per-kernel timing for benchmarks: between profile_begin and profile_end every call on
  * this handle brackets its dominant kernel (the fused log-mel kernel, not the memset / clamp pass)
  * with a pair of CUDA events recorded on the call's stream, up to `max_launches` pairs.
