@@ -79,3 +79,29 @@ def test_meta_shapes():
     assert torch.ops.b200mel.whisper_logmel(w, None).shape == (5, 80, 3000)
     assert torch.ops.b200mel.mel_power(torch.empty(3, 88200, device="meta"), 1e-9).shape == (3, 64, 173)
     assert torch.ops.b200mel.whisper_frame_mask(torch.empty(4, dtype=torch.int32, device="meta")).shape == (4, 3000)
+
+
+def test_host_pack_matches_numpy_cast(lib):
+    """b200mel_host_pack: ragged float64 / float32 clips -> one float32 staging buffer, truncated at max_samples,
+    rows beyond a clip's length untouched; the cast is numpy's (HF:models/whisper/feature_extraction_whisper.py:285-286)."""
+    rng = np.random.default_rng(0)
+    clips = [rng.standard_normal(n) for n in (480000, 5, 0, 123457, 600000)]
+    for dt in (np.float64, np.float32):
+        arrs = [np.ascontiguousarray(c.astype(dt)) for c in clips]
+        n, stride = len(arrs), 480000
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = np.array([len(a) for a in arrs], dtype=np.int64)
+        for threads in (1, 5):
+            dst = np.full((n, stride), 7.0, dtype=np.float32)
+            out = np.zeros(n, dtype=np.int32)
+            st = lib.b200mel_host_pack(ptrs, lens.ctypes.data_as(ctypes.c_void_p), n, int(dt == np.float64), 480000,
+                                       dst.ctypes.data_as(ctypes.c_void_p), stride, out.ctypes.data_as(ctypes.c_void_p), threads)
+            assert st == 0
+            for i, a in enumerate(arrs):
+                L = min(len(a), 480000)
+                assert out[i] == L
+                assert np.array_equal(dst[i, :L], a[:L].astype(np.float32)) and (dst[i, L:] == 7.0).all()
+    # a clip longer than the row is an error, not an overrun
+    bad = lib.b200mel_host_pack(ptrs, lens.ctypes.data_as(ctypes.c_void_p), n, 0, 480000, dst.ctypes.data_as(ctypes.c_void_p),
+                                1000, None, 2)
+    assert bad == -1 and b"longer than dst_stride" in lib.b200mel_last_error()
