@@ -240,7 +240,7 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   if (k32) {
     const int items = batch * CL_PARTS;
     const int grid = items < CL_CTAS_PER_SM * h->sm_count ? items : CL_CTAS_PER_SM * h->sm_count;
-    whisper_clamp_kernel32<<<grid, CL_THREADS, 0, stream>>>(out, (const float*)workspace, batch);
+    whisper_clamp_kernel32<<<grid, CL_THREADS, 0, stream>>>(out, (const float*)workspace, batch, lengths, (long long)stride_samples);
   } else {
     dim3 grid(30, batch);
     whisper_clamp_kernel<<<grid, 256, 0, stream>>>(out, clip_max, batch);

@@ -24,11 +24,14 @@ whisper_clamp_kernel(float* __restrict__ out, const unsigned int* __restrict__ c
 #endif
 constexpr int CL_THREADS = 256, CL_PARTS = 10;
 __global__ void __launch_bounds__(CL_THREADS, 8)
-whisper_clamp_kernel32(float* __restrict__ out, const float* __restrict__ tile_max, int batch) {
+whisper_clamp_kernel32(float* __restrict__ out, const float* __restrict__ tile_max, int batch,
+                       const int* __restrict__ lengths, long long stride) {
   asm volatile("griddepcontrol.launch_dependents;");
   __shared__ float s_red[CL_THREADS / 32];
   constexpr int VEC_PER_PART = W_NMEL * W_NFRAME / 4 / CL_PARTS;       // 6000
+  constexpr int VEC_PER_ROW = W_NFRAME / 4;                            // 750
   const int tid = threadIdx.x;
+  const float y_silent = w_norm_log(1e-10f);
   for (int item = blockIdx.x; item < batch * CL_PARTS; item += gridDim.x) {
     const int clip = item / CL_PARTS, part = item - clip * CL_PARTS;
     float m = 0.0f;
@@ -41,15 +44,35 @@ whisper_clamp_kernel32(float* __restrict__ out, const float* __restrict__ tile_m
 #pragma unroll
     for (int w = 0; w < CL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
     const float thr = w_norm_log(m) - 2.0f;
+    // frames from `fs` on belong to tiles of pure zero padding, which the log-mel kernel did not write: their value is
+    // known without reading (the silent tiles are a suffix of the clip: v_tile_silent is monotone in f0)
+    const long long len_ll = lengths ? (long long)lengths[clip] : stride;
+    const int L = (int)(len_ll < 0 ? 0 : (len_ll > W_NSAMP ? W_NSAMP : len_ll));
+    int fs = W_NFRAME;
+    for (int f0 = (V_TILES_PER_CLIP - 1) * V_TILE; f0 >= 0 && v_tile_silent(f0, L); f0 -= V_TILE) fs = f0;
+    const float ys = fmaxf(y_silent, thr);
+    const float4 fill = make_float4(ys, ys, ys, ys);
     float4* p = reinterpret_cast<float4*>(out + (size_t)clip * (W_NMEL * W_NFRAME)) + part * VEC_PER_PART;
     for (int i0 = tid; i0 < VEC_PER_PART; i0 += 4 * CL_THREADS) {
       float4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (i0 + j * CL_THREADS < VEC_PER_PART) v[j] = p[i0 + j * CL_THREADS];
+      bool sil[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int i = i0 + j * CL_THREADS;
-        if (i < VEC_PER_PART && (v[j].x < thr || v[j].y < thr || v[j].z < thr || v[j].w < thr)) {
+        sil[j] = true;
+        if (i < VEC_PER_PART) {
+          const int frame = ((part * VEC_PER_PART + i) % VEC_PER_ROW) * 4;       // fs is a multiple of 32
+          sil[j] = frame >= fs;
+          if (!sil[j]) v[j] = p[i];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * CL_THREADS;
+        if (i >= VEC_PER_PART) continue;
+        if (sil[j]) {
+          p[i] = fill;
+        } else if (v[j].x < thr || v[j].y < thr || v[j].z < thr || v[j].w < thr) {
           v[j].x = fmaxf(v[j].x, thr); v[j].y = fmaxf(v[j].y, thr); v[j].z = fmaxf(v[j].z, thr); v[j].w = fmaxf(v[j].w, thr);
           p[i] = v[j];
         }

@@ -29,6 +29,16 @@ constexpr int V_SM_P = W_PROWS * V_COLS * 2;                                    
 constexpr int V_SMEM_BYTES = (V_SM_AUDIO + V_SM_E + V_SM_P + W_SM_TAB) * 4 + 16;
 static_assert(2 * (V_SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs must fit in one SM");
 
+// Does the 32-frame tile starting at frame f0 of a clip with L valid samples see only zero padding?  The smallest
+// clip index any of its rows maps to (left reflection reaches index 0; right reflection maps g >= 480000 to
+// 959998 - g) is already past the clip.
+__device__ __forceinline__ bool v_tile_silent(int f0, int L) {
+  const long long g0 = (long long)f0 * W_HOP - W_NFFT / 2, gend = g0 + V_ROWS * W_HOP;
+  long long jmin = g0 < 0 ? 0 : g0;
+  if (gend > W_NSAMP) { const long long r = 2LL * (W_NSAMP - 1) - (gend - 1); jmin = r < jmin ? r : jmin; }
+  return jmin >= L;
+}
+
 __device__ __forceinline__ WTile v_tile(const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
                                         int tile, int use_tma) {
   WTile t;
@@ -39,13 +49,10 @@ __device__ __forceinline__ WTile v_tile(const float* __restrict__ wave, long lon
   t.src = wave + (size_t)t.clip * (size_t)stride;
   const long long g0 = (long long)t.f0 * W_HOP - W_NFFT / 2, gend = g0 + V_ROWS * W_HOP;
   t.tma = use_tma && g0 >= 0 && gend <= t.L && gend + 4 <= stride;
-  // Smallest clip index any row of the tile maps to (left reflection reaches index 0; right reflection maps
-  // g >= 480000 to 959998 - g).  If that is already past the clip, the tile sees only zero padding: its frames are
-  // exactly the floor value and neither the audio copy nor the FFT is needed.  Whisper inputs are mostly much
-  // shorter than the 30 s they are padded to, so for real batches this is the common tile.
-  long long jmin = g0 < 0 ? 0 : g0;
-  if (gend > W_NSAMP) { const long long r = 2LL * (W_NSAMP - 1) - (gend - 1); jmin = r < jmin ? r : jmin; }
-  t.silent = jmin >= t.L;
+  // A tile that sees only zero padding has exactly the floor value in every feature: neither the audio copy nor the
+  // FFT is needed, and the floor pass writes its features (it knows the final clip maximum).  Whisper inputs are
+  // mostly much shorter than the 30 s they are padded to, so for real batches this is the common tile.
+  t.silent = v_tile_silent(t.f0, t.L);
   return t;
 }
 
@@ -57,16 +64,10 @@ __device__ __forceinline__ float* v_slot(float* __restrict__ tile_max, int clip,
   return tile_max + (size_t)clip * V_SLOTS_PER_CLIP + (f0 / V_TILE) * V_SLOT_WARPS + warp;
 }
 
-// A tile of pure zero padding: mel = 0 -> max(., 1e-10) -> the same w_norm_log as the computed path (all 8 warps).
+// A tile of pure zero padding: its features are written by the floor pass; here only its maximum (mel = 0 ->
+// max(., 1e-10)) is recorded so that an all-silent clip still has a defined clip maximum.
 __device__ __forceinline__ void v_write_silent(const WTile& t, int warp, int lane, float* __restrict__ out,
                                                float* __restrict__ tile_max) {
-  const int frame = t.f0 + lane;
-  const float y = w_norm_log(1e-10f);
-  if (frame < W_NFRAME) {
-    float* out_col = out + (size_t)t.clip * (W_NMEL * W_NFRAME) + frame;
-#pragma unroll 5
-    for (int m = warp; m < W_NMEL; m += V_ALL_WARPS) out_col[(size_t)m * W_NFRAME] = y;
-  }
   if (lane == 0 && warp < V_SLOT_WARPS) *v_slot(tile_max, t.clip, t.f0, warp) = 1e-10f;
 }
 
