@@ -79,8 +79,8 @@ const char* b200mel_last_error(void);
 int b200mel_create(int device, int preset, b200mel_handle** out);
 int b200mel_destroy(b200mel_handle* h);
 
-/* Bytes of device workspace a call with `batch` clips needs (per-clip reduction slots and
- * scheduler words).  The workspace needs no initialisation by the caller. */
+/* Bytes of device workspace a call with `batch` clips needs (per-tile maxima the clip-floor pass reduces,
+ * 94 x 8 floats per clip).  The workspace needs no initialisation by the caller. */
 size_t b200mel_workspace_bytes(const b200mel_handle* h, int32_t batch);
 
 /* Whisper preset.
@@ -136,7 +136,7 @@ int b200mel_host_pack(const void* const* clips, const int64_t* lengths, int32_t 
                       int64_t max_samples, float* dst, int64_t dst_stride, int32_t* out_lengths, int32_t threads);
 
 /* Optional per-kernel timing for benchmarks: between profile_begin and profile_end every call on
- * this handle brackets its dominant kernel (the fused log-mel kernel, not the memset / clamp pass)
+ * this handle brackets its dominant kernel (the fused log-mel kernel, not the clip-floor pass)
  * with a pair of CUDA events recorded on the call's stream, up to `max_launches` pairs.
  * profile_end waits for the recorded events, returns the summed kernel time in milliseconds and the
  * number of launches covered, and switches profiling off again.  Not CUDA-graph capturable and not
