@@ -213,7 +213,7 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
   if (k32) {
     const long long nt = (long long)batch * V_TILES_PER_CLIP;
-    const int grid32 = nt < 2LL * h->sm_count ? (int)nt : 2 * h->sm_count;
+    const int grid32 = nt < (long long)h->sm_count ? (int)nt : h->sm_count;     // one 512-thread CTA (two halves) per SM
     // programmatic stream serialisation: the kernel may begin while the previous kernel of the stream is finishing
     // (it waits with griddepcontrol.wait before its first global write); with profiling on the event records sit
     // between the kernels and switch the overlap off

@@ -12,12 +12,8 @@
 //   mel      a warp takes the 16 columns unpacked: lanes 0..15 the first frame of each pair, lanes 16..31 the
 //            second, scalar FFMA with the same immediates (the FMA pipe time per frame is unchanged).
 // ================================================================================================
-#ifndef V_MEL_WARPS
-#define V_MEL_WARPS 0      // 4: four extra warps own the mel stage (setmaxnreg 96 / 48); measured slower (808 k vs 935 k clips/s), see DESIGN.md
-#endif
-constexpr int V_TILE = 32, V_WARPS = 8;                                          // V_WARPS: DFT warps (pass 1 / pass 2)
-constexpr int V_ALL_WARPS = V_WARPS + V_MEL_WARPS, V_THREADS = V_ALL_WARPS * 32;
-constexpr int V_SLOT_WARPS = V_MEL_WARPS ? V_MEL_WARPS : V_WARPS;                // warps that write a per-tile maximum
+constexpr int V_TILE = 32, V_WARPS = 8;                                          // per half: 8 warps, one 32-frame tile in flight
+constexpr int V_HALVES = 2, V_HALF_THREADS = V_WARPS * 32, V_THREADS = V_HALVES * V_HALF_THREADS;
 constexpr int V_TILES_PER_CLIP = (W_NFRAME + V_TILE - 1) / V_TILE;               // 94
 constexpr int V_ROWS = ((V_TILE - 1) * W_HOP + W_NFFT + W_HOP - 1) / W_HOP;      // 34
 constexpr int V_COLS = V_TILE / 2;                                               // 16 float2 columns
@@ -26,8 +22,10 @@ constexpr int V_TX_BYTES = V_ROWS * W_PITCH * 4;
 constexpr int V_EBLK = 26 * V_COLS + 8;                                          // float2 per class block (+8: two classes of a half-warp store to different banks)
 constexpr int V_SM_E = 16 * V_EBLK * 2;                                          // floats
 constexpr int V_SM_P = W_PROWS * V_COLS * 2;                                     // floats
-constexpr int V_SMEM_BYTES = (V_SM_AUDIO + V_SM_E + V_SM_P + W_SM_TAB) * 4 + 16;
-static_assert(2 * (V_SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs must fit in one SM");
+constexpr int V_HALF_FLOATS = V_SM_AUDIO + V_SM_E + V_SM_P;                        // one half's audio | E | P
+static_assert((V_HALF_FLOATS * 4) % 128 == 0, "the second half's audio tile must stay 128-byte aligned for TMA");
+constexpr int V_SMEM_BYTES = (V_HALVES * V_HALF_FLOATS + W_SM_TAB) * 4 + 64;        // + two mbarriers and the tile counter
+static_assert(V_SMEM_BYTES <= 227 * 1024, "both halves must fit in one SM");
 
 // Does the 32-frame tile starting at frame f0 of a clip with L valid samples see only zero padding?  The smallest
 // clip index any of its rows maps to (left reflection reaches index 0; right reflection maps g >= 480000 to
@@ -59,16 +57,16 @@ __device__ __forceinline__ WTile v_tile(const float* __restrict__ wave, long lon
 // Workspace of this kernel: one float per (clip, tile, warp) = the largest mel energy that warp saw in that tile.
 // Every slot is written exactly once per launch, so the workspace needs no zeroing (no memset node, no atomics),
 // and the clip-floor pass reduces a clip's 94 x 8 slots itself.
-constexpr int V_SLOTS_PER_CLIP = V_TILES_PER_CLIP * V_SLOT_WARPS;
+constexpr int V_SLOTS_PER_CLIP = V_TILES_PER_CLIP * V_WARPS;
 __device__ __forceinline__ float* v_slot(float* __restrict__ tile_max, int clip, int f0, int warp) {
-  return tile_max + (size_t)clip * V_SLOTS_PER_CLIP + (f0 / V_TILE) * V_SLOT_WARPS + warp;
+  return tile_max + (size_t)clip * V_SLOTS_PER_CLIP + (f0 / V_TILE) * V_WARPS + warp;
 }
 
 // A tile of pure zero padding: its features are written by the floor pass; here only its maximum (mel = 0 ->
-// max(., 1e-10)) is recorded so that an all-silent clip still has a defined clip maximum.
-__device__ __forceinline__ void v_write_silent(const WTile& t, int warp, int lane, float* __restrict__ out,
-                                               float* __restrict__ tile_max) {
-  if (lane == 0 && warp < V_SLOT_WARPS) *v_slot(tile_max, t.clip, t.f0, warp) = 1e-10f;
+// max(., 1e-10)) is recorded so that an all-silent clip still has a defined clip maximum.  Called by ONE thread.
+__device__ __forceinline__ void v_record_silent(const WTile& t, float* __restrict__ tile_max) {
+#pragma unroll
+  for (int w = 0; w < V_WARPS; ++w) *v_slot(tile_max, t.clip, t.f0, w) = 1e-10f;
 }
 
 __device__ __forceinline__ void v_stage_generic(const WTile& t, float* __restrict__ s_audio, int part, int nparts, int lane) {
@@ -182,19 +180,9 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
   const float* pl = reinterpret_cast<const float*>(s_p) + 2 * col + half;
   float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame;
   float emax = 0.0f;
-#if V_MEL_WARPS == 4
-  // four dedicated mel warps (`warp` = 0..3 here), eight of 32 cost-balanced shares each: a share's bins fit 40 registers
-#define V_MEL_CASE(w) case w: v_mel_share<w, 32>(pl, out_col, valid, emax); v_mel_share<w + 4, 32>(pl, out_col, valid, emax); \
-    v_mel_share<w + 8, 32>(pl, out_col, valid, emax); v_mel_share<w + 12, 32>(pl, out_col, valid, emax); \
-    v_mel_share<w + 16, 32>(pl, out_col, valid, emax); v_mel_share<w + 20, 32>(pl, out_col, valid, emax); \
-    v_mel_share<w + 24, 32>(pl, out_col, valid, emax); v_mel_share<w + 28, 32>(pl, out_col, valid, emax); break;
-  switch (warp) { V_MEL_CASE(0) V_MEL_CASE(1) V_MEL_CASE(2) default: V_MEL_CASE(3) }
-#undef V_MEL_CASE
-#else
 #define V_MEL_CASE(w) case w: v_mel_share<2 * w, 16>(pl, out_col, valid, emax); v_mel_share<2 * w + 1, 16>(pl, out_col, valid, emax); break;
   switch (warp) { V_MEL_CASE(0) V_MEL_CASE(1) V_MEL_CASE(2) V_MEL_CASE(3) V_MEL_CASE(4) V_MEL_CASE(5) V_MEL_CASE(6) default: V_MEL_CASE(7) }
 #undef V_MEL_CASE
-#endif
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   if (lane == 0) *v_slot(tile_max, clip, f0, warp) = emax;
@@ -210,147 +198,125 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
 #define V_MEL_FIRST(w) (((w) >> 2) & 1)
 #endif
 
-// The tile loop of one warp.  ROLE 0: the warp does everything (no dedicated mel warps); ROLE 1: DFT warp (pass 1,
-// pass 2, TMA issue); ROLE 2: mel warp.  With dedicated mel warps the two roles run this loop as two separate
-// instantiations, so that each gets its own register allocation (96 / 48 after setmaxnreg); both walk the same tile
-// sequence and meet at the same two block barriers per tile.
-template <int ROLE>
+// One 512-thread CTA per SM runs TWO independent halves (8 warps each, own audio / E / P buffers, own named barrier
+// and mbarrier): while one half waits at its barrier or on shared-memory loads the other computes.  The halves draw
+// tiles from a counter in shared memory, so they finish together whatever share of the issue slots each one gets
+// (as two separate CTAs with a static split, the CTA the hardware favoured finished 26 % early and left its SM
+// half empty for the rest of the kernel).  CTA c owns tiles c, c + gridDim, c + 2 gridDim, ...
+template <int DUMMY>
 __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, const float* __restrict__ wave, long long stride,
                                       const int* __restrict__ lengths, int batch, float* __restrict__ out,
                                       float* __restrict__ tile_max, float* smem) {
-  float* s_audio = smem;
-  float2* s_e = reinterpret_cast<float2*>(smem + V_SM_AUDIO);
-  float2* s_p = reinterpret_cast<float2*>(smem + V_SM_AUDIO + V_SM_E);
-  const int* s_off = reinterpret_cast<const int*>(smem + V_SM_AUDIO + V_SM_E + V_SM_P);
-  const float* s_win = smem + V_SM_AUDIO + V_SM_E + V_SM_P + 16 * 28;
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + V_SM_AUDIO + V_SM_E + V_SM_P + W_SM_TAB);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = threadIdx.x >> 8, tid = threadIdx.x & (V_HALF_THREADS - 1), lane = tid & 31, warp = tid >> 5;
+  float* s_audio = smem + half * V_HALF_FLOATS;
+  float2* s_e = reinterpret_cast<float2*>(s_audio + V_SM_AUDIO);
+  float2* s_p = reinterpret_cast<float2*>(s_audio + V_SM_AUDIO + V_SM_E);
+  const int* s_off = reinterpret_cast<const int*>(smem + V_HALVES * V_HALF_FLOATS);
+  const float* s_win = smem + V_HALVES * V_HALF_FLOATS + 16 * 28;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB) + half;
+  int* s_ctl = reinterpret_cast<int*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB) + 4;   // [0] tile counter, [1 + half] next tile
   const int ntiles = batch * V_TILES_PER_CLIP;
+  auto half_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(V_HALF_THREADS) : "memory"); };
 
   // pass-1 role: class a = 4 (warp & 3) + lane / 8, frame pair (16 fg + i, 16 fg + 8 + i) = column 8 fg + i, fg = warp >> 2
   const int p1_a = 4 * (warp & 3) + (lane >> 3);
-  const float* audio_lane = s_audio + (16 * ((warp >> 2) & 1) + (lane & 7)) * W_PITCH;
-  float2* p1_dst = s_e + p1_a * V_EBLK + 8 * ((warp >> 2) & 1) + (lane & 7);
-  // pass-2 role: warps 0..5 take tasks k2 = 1 + 2 warp + lane / 16, warp 6 the real task k2 = 0 (lanes 0..15), warp 7 none
-  // The second CTA of an SM (CTAs are dealt round-robin, so blockIdx >= gridDim / 2) rotates the roles by two warps:
-  // the light pass-2 warps (real task, idle) then sit on the schedulers that carry two full tasks in the first CTA.
-  const int rot = (V_ROTATE && blockIdx.x >= (gridDim.x >> 1)) ? 2 : 0;
-  const int p2_warp = (warp + rot) & 7;
+  const float* audio_lane = s_audio + (16 * (warp >> 2) + (lane & 7)) * W_PITCH;
+  float2* p1_dst = s_e + p1_a * V_EBLK + 8 * (warp >> 2) + (lane & 7);
+  // pass-2 role: warps 0..5 take tasks k2 = 1 + 2 warp + lane / 16, warp 6 the real task k2 = 0 (lanes 0..15), warp 7 none.
+  // The second half rotates the roles by two warps: its light warps (real task, idle) then sit on the schedulers that
+  // carry two full tasks of the first half.
+  const int p2_warp = (warp + (V_ROTATE ? 2 * half : 0)) & 7;
   const int p2_col = lane & 15;
   const int p2_k2 = 1 + 2 * p2_warp + (lane >> 4);
   const bool mel_first = V_MEL_FIRST(warp);
   constexpr int STAGE_TID = 7 * 32;
 
-  // first tile at or after `t` (stride gridDim) that needs computing; tiles of pure zero padding on the way are
-  // written out immediately (by all warps of both roles), so the pipeline below only ever sees tiles with audio in them
-  auto next_tile = [&](int t, WTile& wt) -> int {
-    for (; t < ntiles; t += gridDim.x) {
-      wt = v_tile(wave, stride, lengths, t, use_tma);
-      if (!wt.silent) break;
-      v_write_silent(wt, warp, lane, out, tile_max);
+  // Draw tiles from the shared counter until one has audio in it (tiles of pure zero padding only get their maximum
+  // recorded); for that one, pull its TMA box into L2 already.  Called by ONE thread of the half.
+  auto draw = [&]() -> int {
+    for (;;) {
+      const int t = blockIdx.x + atomicAdd(s_ctl, 1) * gridDim.x;
+      if (t >= ntiles) return ntiles;
+      const WTile wt = v_tile(wave, stride, lengths, t, use_tma);
+      if (!wt.silent) {
+#if V_L2_PREFETCH
+        if (wt.tma) tma_prefetch_l2_3d(tmap, 120, wt.f0 - 2, wt.clip);
+#endif
+        return t;
+      }
+      v_record_silent(wt, tile_max);
     }
-    return t;
   };
   auto stage = [&](const WTile& wt) -> bool {
     if (wt.tma) {
-      if (ROLE != 2 && tid == STAGE_TID) {
+      if (tid == STAGE_TID) {
         fence_proxy_async();
         mbar_arrive_expect_tx(s_bar, V_TX_BYTES);
         tma_load_3d(s_audio, tmap, 120, wt.f0 - 2, wt.clip, s_bar);
       }
     } else {
-      v_stage_generic(wt, s_audio, warp, V_ALL_WARPS, lane);
+      v_stage_generic(wt, s_audio, warp, V_WARPS, lane);
     }
     return wt.tma;
   };
 
-  WTile wt;
-  int tile = next_tile(blockIdx.x, wt);
+  if (tid == STAGE_TID) s_ctl[1 + half] = draw();
+  half_sync();
+  int tile = s_ctl[1 + half];
   unsigned tma_parity = 0;
   bool cur_tma = false;
-  if (tile < ntiles) cur_tma = stage(wt);
+  if (tile < ntiles) cur_tma = stage(v_tile(wave, stride, lengths, tile, use_tma));
   int prev_clip = -1, prev_f0 = 0;
 
   for (;;) {
     const bool have = tile < ntiles;
-    if (ROLE != 2 && have && cur_tma) { mbar_wait(s_bar, tma_parity); tma_parity ^= 1u; }
-    __syncthreads();                       // audio(tile) visible; P(previous tile) complete; E is free
-#if V_L2_PREFETCH
-    // The copy of the next tile can only be issued once pass 1 has released the audio buffer (phase B), which leaves
-    // it one phase to arrive; pulling its box into L2 a phase earlier takes the DRAM latency off that path.
-    if (ROLE != 2 && tid == STAGE_TID && have) {
-      const int nx = tile + gridDim.x;
-      if (nx < ntiles) {
-        const WTile pt = v_tile(wave, stride, lengths, nx, use_tma);
-        if (pt.tma) tma_prefetch_l2_3d(tmap, 120, pt.f0 - 2, pt.clip);
-      }
-    }
-#endif
+    if (have && cur_tma) { mbar_wait(s_bar, tma_parity); tma_parity ^= 1u; }
+    half_sync();                           // audio(tile) visible; P(previous tile) complete; E is free; s_ctl consumed
+    // the tile after this one is drawn now (one thread; the L2 prefetch of its box goes out with it) and published to the
+    // half through shared memory; it is read after the barrier that ends phase A
+    if (tid == STAGE_TID) s_ctl[1 + half] = have ? draw() : ntiles;
 
     // ---- phase A: mel(previous tile) + pass 1(this tile) ----------------------------------------------
-    if (ROLE == 2) {
-      if (prev_clip >= 0) v_mel_phase(warp - V_WARPS, lane, prev_clip, prev_f0, s_p, out, tile_max);
-    } else if (ROLE == 1) {
-      if (have) v_pass1(p1_a, audio_lane, p1_dst, s_off, s_win);
-    } else {
 #pragma unroll 1
-      for (int step = 0; step < 2; ++step) {
-        if ((step == 0) == mel_first) {
-          if (prev_clip >= 0) v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, tile_max);
-        } else if (have) {
-          v_pass1(p1_a, audio_lane, p1_dst, s_off, s_win);
-        }
+    for (int step = 0; step < 2; ++step) {
+      if ((step == 0) == mel_first) {
+        if (prev_clip >= 0) v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, tile_max);
+      } else if (have) {
+        v_pass1(p1_a, audio_lane, p1_dst, s_off, s_win);
       }
     }
     if (!have) break;
-    __syncthreads();                       // E complete; the audio tile and P are dead from here on
+    half_sync();                           // E complete; the audio tile and P are dead from here on
 
-    // ---- phase B: TMA prefetch of the next tile + pass 2(this tile) -----------------------------------
-    const int next = next_tile(tile + gridDim.x, wt);
-    cur_tma = (next < ntiles) ? stage(wt) : false;
-    if (ROLE != 2) {
-      if (p2_warp < 6) v_pass2(p2_k2, s_e + p2_col, s_p + p2_col);
-      else if (p2_warp == 6 && lane < 16) v_pass2_real(s_e + p2_col, s_p + p2_col);
-    }
+    // ---- phase B: copy of the next tile (TMA, or plain stores at a clip edge) + pass 2(this tile) -------
+    const int next = s_ctl[1 + half];
+    cur_tma = (next < ntiles) ? stage(v_tile(wave, stride, lengths, next, use_tma)) : false;
+    if (p2_warp < 6) v_pass2(p2_k2, s_e + p2_col, s_p + p2_col);
+    else if (p2_warp == 6 && lane < 16) v_pass2_real(s_e + p2_col, s_p + p2_col);
     prev_clip = tile / V_TILES_PER_CLIP;
     prev_f0 = (tile - prev_clip * V_TILES_PER_CLIP) * V_TILE;
     tile = next;
   }
 }
 
-#if V_MEL_WARPS
-__global__ void __maxnreg__(80)                                     // setmaxnreg needs an explicit launch-time register count
-#else
-__global__ void __launch_bounds__(V_THREADS, 2)
-#endif
+__global__ void __launch_bounds__(V_THREADS, 1)
 whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
                         const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
                         int batch, float* __restrict__ out, float* __restrict__ tile_max) {
   extern __shared__ __align__(1024) float smem[];
   {
-    int* s_off = reinterpret_cast<int*>(smem + V_SM_AUDIO + V_SM_E + V_SM_P);
-    float* s_win = smem + V_SM_AUDIO + V_SM_E + V_SM_P + 16 * 28;
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + V_SM_AUDIO + V_SM_E + V_SM_P + W_SM_TAB);
+    int* s_off = reinterpret_cast<int*>(smem + V_HALVES * V_HALF_FLOATS);
+    float* s_win = smem + V_HALVES * V_HALF_FLOATS + 16 * 28;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB);
+    int* s_ctl = reinterpret_cast<int*>(s_bar) + 4;
     for (int i = threadIdx.x; i < 16 * 28; i += V_THREADS) { s_off[i] = c_wp1_off[i]; s_win[i] = c_wp1_win[i]; }
-    if (threadIdx.x == 0) { mbar_init(s_bar, 1); fence_proxy_async(); }
+    if (threadIdx.x == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); fence_proxy_async(); s_ctl[0] = 0; }
   }
   __syncthreads();
   // The kernel is launched with programmatic stream serialisation: it may become resident and run its prologue
-  // (tables, mbarrier: nothing that touches global memory) while the previous kernel of the stream -- the clip-floor
+  // (tables, mbarriers: nothing that touches global memory) while the previous kernel of the stream -- the clip-floor
   // pass of the previous call, or whatever produced the audio -- is still finishing.  Everything after this wait sees
   // that kernel's results; nothing before it reads or writes global memory.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-#if V_MEL_WARPS
-  // Warps 0..7 run the two DFT passes (about 95 live registers), warps 8..11 only the mel stage.  The CTA is launched
-  // at 80 registers per thread (2 CTAs x 384 threads) and re-split 8 x 32 x 96 + 4 x 32 x 48 = 12 x 32 x 80.
-  if ((threadIdx.x >> 5) >= V_WARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    v_run<2>(&tmap, use_tma, wave, stride, lengths, batch, out, tile_max, smem);
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
-    v_run<1>(&tmap, use_tma, wave, stride, lengths, batch, out, tile_max, smem);
-  }
-#else
   v_run<0>(&tmap, use_tma, wave, stride, lengths, batch, out, tile_max, smem);
-#endif
 }
