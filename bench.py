@@ -220,14 +220,37 @@ def run_ours(args) -> dict | None:
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") ---------------------------------------------------------
+    # One step = the public op on one resident 64-clip batch.  The calls are captured once per input batch into CUDA
+    # graphs and replayed: the host side of an eager call is ~50 us of Python against ~85 us of GPU work, so an eager
+    # loop measures the host's mood as much as the kernels.  (The C ABI is capturable: no allocation, no sync.)
     for w in range(W):
         ops.whisper_logmel(dev_pool[w % N_POOL], None)
+    barrier()
+    launch_mode = "cuda graph replay (one graph per input batch, captured from the public op)"
+    try:
+        graphs = []
+        for p in range(N_POOL):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                o = ops.whisper_logmel(dev_pool[p], None)
+            graphs.append((g, o))
+
+        def step(k):
+            graphs[k % N_POOL][0].replay()
+            return graphs[k % N_POOL][1]
+    except Exception as exc:  # pragma: no cover - capture unsupported: time the eager calls
+        launch_mode = f"eager calls (graph capture failed: {type(exc).__name__})"
+
+        def step(k):
+            return ops.whisper_logmel(dev_pool[k % N_POOL], None)
+    for w in range(max(W, 3)):
+        step(w)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start = time.perf_counter()
     e0.record()
     for k in range(K):
-        out = ops.whisper_logmel(dev_pool[k % N_POOL], None)
+        out = step(k)
     e1.record()
     barrier()
     t_end = time.perf_counter()
@@ -320,7 +343,7 @@ def run_ours(args) -> dict | None:
         "config": {"workload": f"whisper-tiny 80-mel log-mel, {B} x 30 s 16 kHz clips per GPU per step (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": f"inputs rotate over {N_POOL} distinct {B * 1.92:.0f} MB batches (> 126 MB L2)",
-                   "timing": "CUDA events on the launch stream, max over ranks",
+                   "timing": "CUDA events on the launch stream, max over ranks", "launch": launch_mode,
                    "e2e_steps": Ke, "e2e_wall_s": round(e2e_wall, 4), "checksum": checksum,
                    "gpu_launches_scope": "per rank and step: fused log-mel kernel (TMA-fed) + clip-floor pass; no memset"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
