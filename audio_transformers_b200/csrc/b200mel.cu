@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
 #include <thread>
 #include <vector>
 
@@ -38,6 +40,7 @@ namespace {
 #include "whisper_tile32.cuh"
 #include "whisper_post.cuh"
 #include "urban.cuh"
+#include "urban_packed.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Host side
@@ -65,6 +68,7 @@ struct b200mel_handle {
   int preset;
   int sm_count;
   tmap_encode_fn encode = nullptr;   // Whisper preset: TMA descriptor encoder
+  float* uimg = nullptr;             // urban preset: table image of the packed kernel (device)
   // optional benchmark instrumentation (b200mel_profile_begin/end)
   bool prof_on = false;
   int prof_cap = 0, prof_n = 0;
@@ -104,9 +108,23 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
     e = cudaFuncSetAttribute(whisper_logmel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(urban_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM_BYTES);
-  cudaSetDevice(prev);
-  if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute");
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(urban_mel_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES);
+  if (e != cudaSuccess) { cudaSetDevice(prev); return fail_cuda(e, "cudaFuncSetAttribute"); }
   b200mel_handle* h = new b200mel_handle(device, preset, prop.multiProcessorCount);
+  if (preset == B200MEL_PRESET_URBAN) {
+    std::vector<float> img;
+    u2_build_image(img);
+    e = cudaMalloc((void**)&h->uimg, sizeof(float) * U2_IMG);
+    if (e == cudaSuccess) e = cudaMemcpy(h->uimg, img.data(), sizeof(float) * U2_IMG, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      if (h->uimg) cudaFree(h->uimg);
+      delete h;
+      cudaSetDevice(prev);
+      return fail_cuda(e, "b200mel_create: table upload");
+    }
+  }
+  cudaSetDevice(prev);
   if (preset == B200MEL_PRESET_WHISPER) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -131,6 +149,7 @@ static void prof_free(b200mel_handle* h) {
 
 int b200mel_destroy(b200mel_handle* h) {
   if (h) prof_free(h);
+  if (h && h->uimg) cudaFree(h->uimg);
   delete h;
   return B200MEL_OK;
 }
@@ -278,8 +297,16 @@ int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool prof = h->prof_on && h->prof_n < h->prof_cap;
   if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
-  urban_mel_kernel<<<batch * tiles_per_clip, U_THREADS, U_SMEM_BYTES, stream>>>(
-      wave, (long long)stride_samples, n_samples, n_frames, tiles_per_clip, batch, log_eps, out);
+  static const bool v1 = getenv("B200MEL_URBAN_V1") != nullptr;     // first kernel, kept for A/B runs
+  if (v1) {
+    urban_mel_kernel<<<batch * tiles_per_clip, U_THREADS, U_SMEM_BYTES, stream>>>(
+        wave, (long long)stride_samples, n_samples, n_frames, tiles_per_clip, batch, log_eps, out);
+  } else {
+    const long long total_frames = (long long)batch * n_frames;
+    const int n_tiles = (int)((total_frames + 31) / 32);
+    urban_mel_packed_kernel<<<n_tiles < h->sm_count ? n_tiles : h->sm_count, U2_THREADS, U2_SMEM_BYTES, stream>>>(
+        wave, (long long)stride_samples, n_samples, n_frames, total_frames, n_tiles, log_eps, h->uimg, out);
+  }
   if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "urban_mel_kernel launch");

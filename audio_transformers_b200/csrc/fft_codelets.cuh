@@ -371,15 +371,23 @@ B2_HD void rdft32_untangle(const V Zr[16], const V Zi[16], V Xr[17], V Xi[17]) {
 
 // ---- 32-point DFT of REAL (windowed) input, outputs k = 0..16 -----------------------------------
 // Packs z[j] = x[2j] + i x[2j+1], one complex 16-point DFT, then the standard untangling step.
-template <class V, class W>
-B2_HD void real_dft32(const V x[32], const W w[32], V Xr[17], V Xi[17]) {
+// xw: the 32 samples with the window already applied
+template <class V>
+B2_HD void real_dft32_windowed(const V xw[32], V Xr[17], V Xi[17]) {
   V zr[16], zi[16], Zr[16], Zi[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) { zr[j] = vmulc(x[2 * j], w[2 * j]); zi[j] = vmulc(x[2 * j + 1], w[2 * j + 1]); }
+  for (int j = 0; j < 16; ++j) { zr[j] = xw[2 * j]; zi[j] = xw[2 * j + 1]; }
   cplx_dft16(zr, zi, Zr, Zi);
   rdft32_untangle<0>(Zr, Zi, Xr, Xi);
   Xr[16] = vsub(Zr[0], Zi[0]);           // X[16] = sum_even - sum_odd (real)
   Xi[16] = vsub(Zr[0], Zr[0]);           // exact zero of the right type
+}
+template <class V, class W>
+B2_HD void real_dft32(const V x[32], const W w[32], V Xr[17], V Xi[17]) {
+  V xw[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) xw[j] = vmulc(x[j], w[j]);
+  real_dft32_windowed(xw, Xr, Xi);
 }
 
 // ---- Good-Thomas index maps for N = 400 = 16 x 25 ----------------------------------------------
