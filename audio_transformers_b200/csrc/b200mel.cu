@@ -303,9 +303,10 @@ int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples
         wave, (long long)stride_samples, n_samples, n_frames, tiles_per_clip, batch, log_eps, out);
   } else {
     const long long total_frames = (long long)batch * n_frames;
+    if (total_frames > 0x7fffff00LL) return fail(B200MEL_ERR_BAD_ARG, "mel: batch * frames must fit 31 bits");
     const int n_tiles = (int)((total_frames + 31) / 32);
     urban_mel_packed_kernel<<<n_tiles < h->sm_count ? n_tiles : h->sm_count, U2_THREADS, U2_SMEM_BYTES, stream>>>(
-        wave, (long long)stride_samples, n_samples, n_frames, total_frames, n_tiles, log_eps, h->uimg, out);
+        wave, (long long)stride_samples, n_samples, n_frames, (unsigned)total_frames, n_tiles, log_eps, h->uimg, out);
   }
   if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
   cudaError_t e = cudaGetLastError();

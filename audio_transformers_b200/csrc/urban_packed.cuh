@@ -25,8 +25,9 @@
 //    k2 = 1..15.  |X|^2 goes to P[bin][frame].
 //  * mel: 32 half-warp groups share the 64 HTK filters (998 taps, cost-balanced on the host), FFMA2 over the
 //    frame pair, optional log(. + eps), stores straight to out[clip][mel][t].
-//  * schedule per tile: { pass 2 } sync { issue the next tile's audio loads; mel of this tile; pass-1 DFT of
-//    the next tile } sync.  The loads are in flight while the mel phase runs.
+//  * schedule per tile: { pass 2; issue the next tile's audio loads } sync { mel of this tile and pass-1 DFT
+//    of the next tile, in either order: two warps per scheduler run the (LSU-bound) mel first and two the
+//    (FMA-bound) DFT first } sync.  The loads are in flight across the barrier and the first half-phase.
 // All tables come from one image built by b200mel_create (u2_build_image) and copied to shared memory once
 // per CTA.
 // ------------------------------------------------------------------------------------------------
@@ -50,43 +51,53 @@ __device__ __forceinline__ constexpr int u2_row_re(int k2) { return k2 == 0 ? 0 
 
 struct U2Geom {
   const float* __restrict__ wave;
-  long long stride, total_frames;
-  int n_samples, n_frames;
+  long long stride;
+  unsigned total_frames, n_frames;     // flat frame indices fit 32 bits (checked by the host)
+  int n_samples;
 };
 
-// audio of one frame pair (flat frames g, g + 1) -> x[j] = (frame g, frame g + 1) sample r + 32 j
-__device__ __forceinline__ void u2_load_pair(const U2Geom& G, long long g, int r, float2 x[32]) {
-  const long long clip = g / G.n_frames;
-  const int t = (int)(g - clip * G.n_frames);
-  const int base = t * U_HOP - U_NFFT / 2;
+// audio of one frame pair (flat frames g, g + 1) -> x[j] = (frame g, frame g + 1) sample r + 32 j.
+// Returns false (and loads nothing) when the pair needs the generic path below.
+__device__ __forceinline__ bool u2_load_pair(const U2Geom& G, unsigned g, int r, float2 x[32]) {
+  const unsigned clip = g / G.n_frames;
+  const unsigned t = g - clip * G.n_frames;
+  const int base = (int)t * U_HOP - U_NFFT / 2;
   const bool fast = (g + 1 < G.total_frames) && (t + 1 < G.n_frames) && (base >= 0) && (base + U_HOP + U_NFFT <= G.n_samples);
-  if (fast) {
-    const float* __restrict__ p = G.wave + clip * G.stride + base + r;
-    float v[48];
+  if (!fast) return false;
+  const float* __restrict__ p = G.wave + (size_t)clip * G.stride + base + r;
+  float v[48];
 #pragma unroll
-    for (int j = 0; j < 48; ++j) v[j] = __ldg(p + 32 * j);
+  for (int j = 0; j < 48; ++j) v[j] = __ldg(p + 32 * j);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = make_float2(v[j], v[j + 16]);
-    return;
-  }
-  float v[2][32];
-#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] = make_float2(v[j], v[j + 16]);
+  return true;
+}
+
+// Clip edges (reflect padding, no edge repeat), pairs that straddle two clips, the tail of the last tile: 2-3
+// pairs per clip.  The loop over the two frames stays rolled to keep this path small; it passes the samples through the E slots that this
+// lane is about to overwrite with the pair's own DFT (E[r][0..31][2p, 2p+1]; nobody else touches them), so it
+// must run after the barrier that frees E.
+__device__ __forceinline__ void u2_load_pair_generic(const U2Geom& G, unsigned g, int r, int p, float* __restrict__ s_e, float2 x[32]) {
+  float* __restrict__ slot = s_e + r * U2_EP + 2 * p;                // + 32 j + s
+#pragma unroll 1
   for (int s = 0; s < 2; ++s) {
-    const long long gs = g + s;
-    const long long c = gs / G.n_frames;
-    const int ts = (int)(gs - c * G.n_frames);
-    const int b = ts * U_HOP - U_NFFT / 2 + r;
+    const unsigned gs = g + s;
+    const unsigned c = gs / G.n_frames;
+    const int b = (int)(gs - c * G.n_frames) * U_HOP - U_NFFT / 2 + r;
     const bool valid = gs < G.total_frames;
-    const float* __restrict__ p = G.wave + c * G.stride;
+    const float* __restrict__ src = G.wave + (size_t)c * G.stride;
+    float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 32; ++j) {                                   // all 32 loads in flight together
       int i = b + 32 * j;
-      i = i < 0 ? -i : (i >= G.n_samples ? 2 * (G.n_samples - 1) - i : i);      // reflect, no edge repeat
-      v[s][j] = (valid && i >= 0 && i < G.n_samples) ? __ldg(p + i) : 0.0f;
+      i = i < 0 ? -i : (i >= G.n_samples ? 2 * (G.n_samples - 1) - i : i);
+      v[j] = (valid && i >= 0 && i < G.n_samples) ? __ldg(src + i) : 0.0f;
     }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) slot[32 * j + s] = v[j];
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) x[j] = make_float2(v[0][j], v[1][j]);
+  for (int j = 0; j < 32; ++j) x[j] = *reinterpret_cast<const float2*>(slot + 32 * j);
 }
 
 // window, real 32-point DFT over j, store Y_r[k2] for the pair p (frames 2p, 2p + 1 of the tile)
@@ -170,12 +181,14 @@ __device__ __forceinline__ void u2_mel(const U2Geom& G, int tile, int group, int
   const int4* __restrict__ gent = reinterpret_cast<const int4*>(s_img + U2_IMG_GENT);
   const float2* __restrict__ mw2 = reinterpret_cast<const float2*>(s_img + U2_IMG_MW2);
   const float2* __restrict__ p2 = reinterpret_cast<const float2*>(s_p) + q;
-  const long long g0 = (long long)tile * 32 + 2 * q, g1 = g0 + 1;
-  const long long c0 = g0 / G.n_frames, c1 = g1 / G.n_frames;
-  const int t0 = (int)(g0 - c0 * G.n_frames), t1 = (int)(g1 - c1 * G.n_frames);
-  const bool v0 = g0 < G.total_frames, v1 = g1 < G.total_frames;
+  const unsigned g0 = (unsigned)tile * 32u + 2u * q;
+  unsigned c0 = g0 / G.n_frames, t0 = g0 - c0 * G.n_frames;
+  unsigned c1 = c0, t1 = t0 + 1;
+  if (t1 == G.n_frames) { t1 = 0; ++c1; }
+  const bool v0 = g0 < G.total_frames, v1 = g0 + 1 < G.total_frames;
   float* __restrict__ o0 = out + (size_t)c0 * ((size_t)U_NMEL * G.n_frames) + t0;
   float* __restrict__ o1 = out + (size_t)c1 * ((size_t)U_NMEL * G.n_frames) + t1;
+  const bool take_log = log_eps >= 0.0f;
   const int e1 = goff[group + 1];
 #pragma unroll 1
   for (int e = goff[group]; e < e1; ++e) {
@@ -185,15 +198,15 @@ __device__ __forceinline__ void u2_mel(const U2Geom& G, int tile, int group, int
     float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll 4
     for (int j = 0; j < f.y; ++j) acc = b2::vfma(pp[j * 16], ww[j], acc);
-    if (log_eps >= 0.0f) { acc.x = __logf(acc.x + log_eps); acc.y = __logf(acc.y + log_eps); }
-    const size_t mo = (size_t)f.w * G.n_frames;
+    if (take_log) { acc.x = __logf(acc.x + log_eps); acc.y = __logf(acc.y + log_eps); }
+    const unsigned mo = (unsigned)f.w * G.n_frames;
     if (v0) o0[mo] = acc.x;
     if (v1) o1[mo] = acc.y;
   }
 }
 
 __global__ void __launch_bounds__(U2_THREADS, 1)
-urban_mel_packed_kernel(const float* __restrict__ wave, long long stride, int n_samples, int n_frames, long long total_frames,
+urban_mel_packed_kernel(const float* __restrict__ wave, long long stride, int n_samples, int n_frames, unsigned total_frames,
                         int n_tiles, float log_eps, const float* __restrict__ image, float* __restrict__ out) {
   extern __shared__ __align__(1024) float smem[];
   float* s_e = smem;
@@ -201,33 +214,35 @@ urban_mel_packed_kernel(const float* __restrict__ wave, long long stride, int n_
   float* s_img = smem + U2_E + U2_P;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = lane >> 4, q = lane & 15;
+  const bool dft_first = (warp >> 2) & 1;             // two warps of either kind per scheduler
   for (int i = tid; i < U2_IMG / 4; i += U2_THREADS)
     reinterpret_cast<float4*>(s_img)[i] = __ldg(reinterpret_cast<const float4*>(image) + i);
-  U2Geom G{wave, stride, total_frames, n_samples, n_frames};
-  int tile = blockIdx.x;
-  if (tile >= n_tiles) return;
+  U2Geom G{wave, stride, total_frames, (unsigned)n_frames, n_samples};
+  int cur = -1, nxt = blockIdx.x;                     // the first trip has no current tile: it only runs pass 1
   float2 x[32];
-  u2_load_pair(G, (long long)tile * 32 + 2 * warp, lane, x);
-  __syncthreads();                                   // table image in place
-  u2_pass1_dft(x, lane, warp, s_img, s_e);
-  __syncthreads();
 #pragma unroll 1
   for (;;) {
-    if (warp == 0) {
-      u2_pass2_real<0>(h, q, s_img, s_e, s_p);
-      u2_pass2_real<16>(h, q, s_img, s_e, s_p);
-    } else {
-      u2_pass2(warp, h, q, s_img, s_e, s_p);
+    if (cur >= 0) {
+      if (warp == 0) {
+        u2_pass2_real<0>(h, q, s_img, s_e, s_p);
+        u2_pass2_real<16>(h, q, s_img, s_e, s_p);
+      } else {
+        u2_pass2(warp, h, q, s_img, s_e, s_p);
+      }
     }
-    __syncthreads();                                 // P complete, E free
-    const int next = tile + gridDim.x;
-    const bool more = next < n_tiles;
-    if (more) u2_load_pair(G, (long long)next * 32 + 2 * warp, lane, x);
-    u2_mel(G, tile, 2 * warp + h, q, log_eps, s_img, s_p, out);
+    const bool more = nxt < n_tiles;
+    const unsigned g = (unsigned)nxt * 32u + 2u * warp;
+    bool loaded = false;
+    if (more) loaded = u2_load_pair(G, g, lane, x);   // in flight across the barrier
+    __syncthreads();                                  // P complete, E free (first trip: table image in place)
+    if (more && !loaded) u2_load_pair_generic(G, g, lane, warp, s_e, x);
+    if (dft_first && more) u2_pass1_dft(x, lane, warp, s_img, s_e);
+    if (cur >= 0) u2_mel(G, cur, 2 * warp + h, q, log_eps, s_img, s_p, out);
+    if (!dft_first && more) u2_pass1_dft(x, lane, warp, s_img, s_e);
     if (!more) break;
-    u2_pass1_dft(x, lane, warp, s_img, s_e);
-    __syncthreads();                                 // E complete, P free
-    tile = next;
+    __syncthreads();                                  // E complete, P free
+    cur = nxt;
+    nxt += gridDim.x;
   }
 }
 
