@@ -56,48 +56,50 @@ struct U2Geom {
   int n_samples;
 };
 
-// audio of one frame pair (flat frames g, g + 1) -> x[j] = (frame g, frame g + 1) sample r + 32 j.
-// Returns false (and loads nothing) when the pair needs the generic path below.
-__device__ __forceinline__ bool u2_load_pair(const U2Geom& G, unsigned g, int r, float2 x[32]) {
+// L2 prefetch of the 6 KB a frame pair reads (fast-path pairs only; the edge pairs are few)
+__device__ __forceinline__ void u2_prefetch_pair(const U2Geom& G, unsigned g) {
+  if (g + 1 >= G.total_frames) return;
+  const unsigned clip = g / G.n_frames;
+  const unsigned t = g - clip * G.n_frames;
+  const int base = (int)t * U_HOP - U_NFFT / 2;
+  if (t + 1 < G.n_frames && base >= 0 && base + U_HOP + U_NFFT <= G.n_samples)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(G.wave + (size_t)clip * G.stride + base), "r"((U_HOP + U_NFFT) * 4) : "memory");
+}
+
+// audio of one frame pair (flat frames g, g + 1) -> x[j] = (frame g, frame g + 1) sample r + 32 j
+__device__ __forceinline__ void u2_load_pair(const U2Geom& G, unsigned g, int r, float2 x[32]) {
   const unsigned clip = g / G.n_frames;
   const unsigned t = g - clip * G.n_frames;
   const int base = (int)t * U_HOP - U_NFFT / 2;
   const bool fast = (g + 1 < G.total_frames) && (t + 1 < G.n_frames) && (base >= 0) && (base + U_HOP + U_NFFT <= G.n_samples);
-  if (!fast) return false;
-  const float* __restrict__ p = G.wave + (size_t)clip * G.stride + base + r;
-  float v[48];
+  if (fast) {
+    const float* __restrict__ p = G.wave + (size_t)clip * G.stride + base + r;
+    float v[48];
 #pragma unroll
-  for (int j = 0; j < 48; ++j) v[j] = __ldg(p + 32 * j);
+    for (int j = 0; j < 48; ++j) v[j] = __ldg(p + 32 * j);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) x[j] = make_float2(v[j], v[j + 16]);
-  return true;
-}
-
-// Clip edges (reflect padding, no edge repeat), pairs that straddle two clips, the tail of the last tile: 2-3
-// pairs per clip.  The loop over the two frames stays rolled to keep this path small; it passes the samples through the E slots that this
-// lane is about to overwrite with the pair's own DFT (E[r][0..31][2p, 2p+1]; nobody else touches them), so it
-// must run after the barrier that frees E.
-__device__ __forceinline__ void u2_load_pair_generic(const U2Geom& G, unsigned g, int r, int p, float* __restrict__ s_e, float2 x[32]) {
-  float* __restrict__ slot = s_e + r * U2_EP + 2 * p;                // + 32 j + s
-#pragma unroll 1
+    for (int j = 0; j < 32; ++j) x[j] = make_float2(v[j], v[j + 16]);
+    return;
+  }
+  // clip edges (reflect padding, no edge repeat), pairs that straddle two clips, the tail of the last tile:
+  // 2-3 pairs per clip
+  float v[2][32];
+#pragma unroll
   for (int s = 0; s < 2; ++s) {
     const unsigned gs = g + s;
     const unsigned c = gs / G.n_frames;
     const int b = (int)(gs - c * G.n_frames) * U_HOP - U_NFFT / 2 + r;
     const bool valid = gs < G.total_frames;
     const float* __restrict__ src = G.wave + (size_t)c * G.stride;
-    float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {                                   // all 32 loads in flight together
+    for (int j = 0; j < 32; ++j) {
       int i = b + 32 * j;
       i = i < 0 ? -i : (i >= G.n_samples ? 2 * (G.n_samples - 1) - i : i);
-      v[j] = (valid && i >= 0 && i < G.n_samples) ? __ldg(src + i) : 0.0f;
+      v[s][j] = (valid && i >= 0 && i < G.n_samples) ? __ldg(src + i) : 0.0f;
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) slot[32 * j + s] = v[j];
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) x[j] = *reinterpret_cast<const float2*>(slot + 32 * j);
+  for (int j = 0; j < 32; ++j) x[j] = make_float2(v[0][j], v[1][j]);
 }
 
 // window, real 32-point DFT over j, store Y_r[k2] for the pair p (frames 2p, 2p + 1 of the tile)
@@ -231,11 +233,9 @@ urban_mel_packed_kernel(const float* __restrict__ wave, long long stride, int n_
       }
     }
     const bool more = nxt < n_tiles;
-    const unsigned g = (unsigned)nxt * 32u + 2u * warp;
-    bool loaded = false;
-    if (more) loaded = u2_load_pair(G, g, lane, x);   // in flight across the barrier
+    if (more) u2_load_pair(G, (unsigned)nxt * 32u + 2u * warp, lane, x);     // in flight across the barrier
+    if (lane == 0 && nxt + (int)gridDim.x < n_tiles) u2_prefetch_pair(G, (unsigned)(nxt + gridDim.x) * 32u + 2u * warp);
     __syncthreads();                                  // P complete, E free (first trip: table image in place)
-    if (more && !loaded) u2_load_pair_generic(G, g, lane, warp, s_e, x);
     if (dft_first && more) u2_pass1_dft(x, lane, warp, s_img, s_e);
     if (cur >= 0) u2_mel(G, cur, 2 * warp + h, q, log_eps, s_img, s_p, out);
     if (!dft_first && more) u2_pass1_dft(x, lane, warp, s_img, s_e);
