@@ -115,6 +115,7 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
   if (preset == B200MEL_PRESET_URBAN) {
     std::vector<float> img;
     u2_build_image(img);
+    if (img.empty()) { delete h; cudaSetDevice(prev); return fail(B200MEL_ERR_BAD_ARG, "b200mel_create: urban filter table does not fit its image"); }
     e = cudaMalloc((void**)&h->uimg, sizeof(float) * U2_IMG);
     if (e == cudaSuccess) e = cudaMemcpy(h->uimg, img.data(), sizeof(float) * U2_IMG, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {

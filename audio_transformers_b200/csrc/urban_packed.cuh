@@ -38,9 +38,10 @@ constexpr int U2_P = U_NBIN * 32;
 constexpr int U2_NNZ = B200MEL_U_NNZ;                       // 998
 constexpr int U2_IMG_T4 = 0;                                // float4 (c, c, s, s) [17][32][2]
 constexpr int U2_IMG_WIN2 = U2_IMG_T4 + 17 * 32 * 2 * 4;    // float2 (w, w) [1024]
-constexpr int U2_IMG_MW2 = U2_IMG_WIN2 + 2048;              // float2 (w, w) [1000]
-constexpr int U2_IMG_GOFF = U2_IMG_MW2 + 2000;              // int [33] (+ padding to 64)
-constexpr int U2_IMG_GENT = U2_IMG_GOFF + 64;               // int4 (first bin, taps, weight offset, mel) [64]
+constexpr int U2_MW_MAX = 1536;                             // filter weights, every filter padded with zeros to 8 k taps
+constexpr int U2_IMG_MW = U2_IMG_WIN2 + 2048;               // float [U2_MW_MAX]
+constexpr int U2_IMG_GOFF = U2_IMG_MW + U2_MW_MAX;          // int [33] (+ padding to 64)
+constexpr int U2_IMG_GENT = U2_IMG_GOFF + 64;               // int4 (first bin, padded taps, weight offset, mel) [64]
 constexpr int U2_IMG = U2_IMG_GENT + 64 * 4;
 constexpr int U2_SMEM_BYTES = (U2_E + U2_P + U2_IMG) * 4;
 static_assert(U2_SMEM_BYTES <= 227 * 1024, "urban packed kernel: shared memory");
@@ -181,7 +182,7 @@ __device__ __forceinline__ void u2_mel(const U2Geom& G, int tile, int group, int
                                        const float* __restrict__ s_img, const float* __restrict__ s_p, float* __restrict__ out) {
   const int* __restrict__ goff = reinterpret_cast<const int*>(s_img + U2_IMG_GOFF);
   const int4* __restrict__ gent = reinterpret_cast<const int4*>(s_img + U2_IMG_GENT);
-  const float2* __restrict__ mw2 = reinterpret_cast<const float2*>(s_img + U2_IMG_MW2);
+  const float* __restrict__ mw = s_img + U2_IMG_MW;
   const float2* __restrict__ p2 = reinterpret_cast<const float2*>(s_p) + q;
   const unsigned g0 = (unsigned)tile * 32u + 2u * q;
   unsigned c0 = g0 / G.n_frames, t0 = g0 - c0 * G.n_frames;
@@ -196,10 +197,27 @@ __device__ __forceinline__ void u2_mel(const U2Geom& G, int tile, int group, int
   for (int e = goff[group]; e < e1; ++e) {
     const int4 f = gent[e];
     const float2* __restrict__ pp = p2 + f.x * 16;
-    const float2* __restrict__ ww = mw2 + f.z;
-    float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll 4
-    for (int j = 0; j < f.y; ++j) acc = b2::vfma(pp[j * 16], ww[j], acc);
+    const float4* __restrict__ ww = reinterpret_cast<const float4*>(mw + f.z);
+    // 8 taps per trip (the zero padding may read a few rows past the filter, and past P into the tables: finite
+    // values times zero), two accumulation chains
+    float2 a0 = make_float2(0.0f, 0.0f), a1 = a0;
+#pragma unroll 1
+    for (int j = 0; j < f.y; j += 8) {
+      const float4 wa = ww[0], wb = ww[1];
+      float2 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = pp[i * 16];
+      a0.x = __fmaf_rn(v[0].x, wa.x, a0.x); a0.y = __fmaf_rn(v[0].y, wa.x, a0.y);
+      a1.x = __fmaf_rn(v[1].x, wa.y, a1.x); a1.y = __fmaf_rn(v[1].y, wa.y, a1.y);
+      a0.x = __fmaf_rn(v[2].x, wa.z, a0.x); a0.y = __fmaf_rn(v[2].y, wa.z, a0.y);
+      a1.x = __fmaf_rn(v[3].x, wa.w, a1.x); a1.y = __fmaf_rn(v[3].y, wa.w, a1.y);
+      a0.x = __fmaf_rn(v[4].x, wb.x, a0.x); a0.y = __fmaf_rn(v[4].y, wb.x, a0.y);
+      a1.x = __fmaf_rn(v[5].x, wb.y, a1.x); a1.y = __fmaf_rn(v[5].y, wb.y, a1.y);
+      a0.x = __fmaf_rn(v[6].x, wb.z, a0.x); a0.y = __fmaf_rn(v[6].y, wb.z, a0.y);
+      a1.x = __fmaf_rn(v[7].x, wb.w, a1.x); a1.y = __fmaf_rn(v[7].y, wb.w, a1.y);
+      pp += 8 * 16; ww += 2;
+    }
+    float2 acc = make_float2(a0.x + a1.x, a0.y + a1.y);
     if (take_log) { acc.x = __logf(acc.x + log_eps); acc.y = __logf(acc.y + log_eps); }
     const unsigned mo = (unsigned)f.w * G.n_frames;
     if (v0) o0[mo] = acc.x;
@@ -259,28 +277,34 @@ static void u2_build_image(std::vector<float>& img) {
         d[0] = c; d[1] = c; d[2] = s; d[3] = s;
       }
   for (int n = 0; n < 1024; ++n) img[U2_IMG_WIN2 + 2 * n] = img[U2_IMG_WIN2 + 2 * n + 1] = host_tab::c_win1024[n];
-  for (int i = 0; i < U2_NNZ; ++i) img[U2_IMG_MW2 + 2 * i] = img[U2_IMG_MW2 + 2 * i + 1] = host_tab::c_umelw[i];
-  // 64 filters -> 32 groups, longest-processing-time first (cost = 3 per tap + 24 per filter)
-  int order[64], load[32] = {0}, owner[64];
-  for (int m = 0; m < 64; ++m) order[m] = m;
-  std::sort(order, order + 64, [](int a, int b) { return host_tab::kUMelLen[a] != host_tab::kUMelLen[b] ? host_tab::kUMelLen[a] > host_tab::kUMelLen[b] : a < b; });
+  // 64 filters -> 32 half-warp groups, longest-processing-time first (cost = padded taps + 6 per filter)
+  int order[64], load[32] = {0}, owner[64], pad[64];
+  for (int m = 0; m < 64; ++m) { order[m] = m; pad[m] = (host_tab::kUMelLen[m] + 7) / 8 * 8; }
+  std::sort(order, order + 64, [&](int a, int b) { return pad[a] != pad[b] ? pad[a] > pad[b] : a < b; });
   for (int i = 0; i < 64; ++i) {
     int best = 0;
     for (int g = 1; g < 32; ++g) if (load[g] < load[best]) best = g;
     owner[order[i]] = best;
-    load[best] += 3 * host_tab::kUMelLen[order[i]] + 24;
+    load[best] += pad[order[i]] + 6;
   }
+  // the two groups of a warp run in lock step: put groups of similar load side by side
+  int gorder[32];
+  for (int g = 0; g < 32; ++g) gorder[g] = g;
+  std::sort(gorder, gorder + 32, [&](int a, int b) { return load[a] != load[b] ? load[a] > load[b] : a < b; });
   int* goff = reinterpret_cast<int*>(img.data() + U2_IMG_GOFF);
   int* gent = reinterpret_cast<int*>(img.data() + U2_IMG_GENT);
-  int n = 0;
-  for (int g = 0; g < 32; ++g) {
-    goff[g] = n;
+  int n = 0, woff = 0;
+  for (int gi = 0; gi < 32; ++gi) {
+    goff[gi] = n;
     for (int m = 0; m < 64; ++m)
-      if (owner[m] == g) {
-        gent[4 * n + 0] = host_tab::kUMelStart[m]; gent[4 * n + 1] = host_tab::kUMelLen[m];
-        gent[4 * n + 2] = host_tab::kUMelOff[m];   gent[4 * n + 3] = m;
+      if (owner[m] == gorder[gi]) {
+        for (int j = 0; j < host_tab::kUMelLen[m]; ++j) img[U2_IMG_MW + woff + j] = host_tab::c_umelw[host_tab::kUMelOff[m] + j];
+        gent[4 * n + 0] = host_tab::kUMelStart[m]; gent[4 * n + 1] = pad[m];
+        gent[4 * n + 2] = woff;                    gent[4 * n + 3] = m;
+        woff += pad[m];
         ++n;
       }
   }
+  if (woff > U2_MW_MAX) { img.clear(); return; }
   goff[32] = n;
 }
