@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("B200MEL_LIB", os.path.join(_HERE, "libb200mel.so"))   # env override: kernel experiments only
+LIB_PATH = os.environ.get("B200MEL_LIB") or os.path.join(_HERE, "libb200mel.so")   # env override: kernel experiments only
 
 PRESET_WHISPER = 0
 PRESET_URBAN = 1

@@ -24,7 +24,7 @@ constexpr int V_SM_E = 16 * V_EBLK * 2;                                         
 constexpr int V_SM_P = W_PROWS * V_COLS * 2;                                     // floats
 constexpr int V_HALF_FLOATS = V_SM_AUDIO + V_SM_E + V_SM_P;                        // one half's audio | E | P
 static_assert((V_HALF_FLOATS * 4) % 128 == 0, "the second half's audio tile must stay 128-byte aligned for TMA");
-constexpr int V_SMEM_BYTES = (V_HALVES * V_HALF_FLOATS + W_SM_TAB) * 4 + 64;        // + two mbarriers and the tile counter
+constexpr int V_SMEM_BYTES = (V_HALVES * V_HALF_FLOATS + W_SM_TAB) * 4 + 128;       // + two mbarriers, the tile counter, the tile descriptor rings
 static_assert(V_SMEM_BYTES <= 227 * 1024, "both halves must fit in one SM");
 
 // Does the 32-frame tile starting at frame f0 of a clip with L valid samples see only zero padding?  The smallest
@@ -216,7 +216,9 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
   const int* s_off = reinterpret_cast<const int*>(smem + V_HALVES * V_HALF_FLOATS);
   const float* s_win = smem + V_HALVES * V_HALF_FLOATS + 16 * 28;
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB) + half;
-  int* s_ctl = reinterpret_cast<int*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB) + 4;   // [0] tile counter, [1 + half] next tile
+  int* s_ctl = reinterpret_cast<int*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB) + 4;   // tile counter
+  // two-slot ring of drawn tiles per half: {tile, clip, first frame, valid samples | TMA flag << 30}
+  int4* s_desc = reinterpret_cast<int4*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB + 8) + 2 * half;
   const int ntiles = batch * V_TILES_PER_CLIP;
   auto half_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(V_HALF_THREADS) : "memory"); };
 
@@ -234,20 +236,27 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
   constexpr int STAGE_TID = 7 * 32;
 
   // Draw tiles from the shared counter until one has audio in it (tiles of pure zero padding only get their maximum
-  // recorded); for that one, pull its TMA box into L2 already.  Called by ONE thread of the half.
-  auto draw = [&]() -> int {
+  // recorded); for that one, pull its TMA box into L2 already.  Called by ONE thread of the half, which publishes
+  // the descriptor through shared memory: nobody else divides, reads the clip length or classifies the tile.
+  auto draw = [&]() -> int4 {
     for (;;) {
       const int t = blockIdx.x + atomicAdd(s_ctl, 1) * gridDim.x;
-      if (t >= ntiles) return ntiles;
+      if (t >= ntiles) return make_int4(ntiles, 0, 0, 0);
       const WTile wt = v_tile(wave, stride, lengths, t, use_tma);
       if (!wt.silent) {
 #if V_L2_PREFETCH
         if (wt.tma) tma_prefetch_l2_3d(tmap, 120, wt.f0 - 2, wt.clip);
 #endif
-        return t;
+        return make_int4(t, wt.clip, wt.f0, wt.L | (wt.tma ? 0x40000000 : 0));
       }
       v_record_silent(wt, tile_max);
     }
+  };
+  auto unpack = [&](const int4& d) -> WTile {
+    WTile wt;
+    wt.clip = d.y; wt.f0 = d.z; wt.L = d.w & 0x3fffffff; wt.tma = (d.w >> 30) & 1; wt.silent = false;
+    wt.src = wave + (size_t)d.y * (size_t)stride;
+    return wt;
   };
   auto stage = [&](const WTile& wt) -> bool {
     if (wt.tma) {
@@ -262,21 +271,19 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
     return wt.tma;
   };
 
-  if (tid == STAGE_TID) s_ctl[1 + half] = draw();
+  if (tid == STAGE_TID) { s_desc[0] = draw(); s_desc[1] = draw(); }
   half_sync();
-  int tile = s_ctl[1 + half];
+  int4 cur = s_desc[0];
   unsigned tma_parity = 0;
   bool cur_tma = false;
-  if (tile < ntiles) cur_tma = stage(v_tile(wave, stride, lengths, tile, use_tma));
+  if (cur.x < ntiles) cur_tma = stage(unpack(cur));
   int prev_clip = -1, prev_f0 = 0;
 
-  for (;;) {
-    const bool have = tile < ntiles;
+#pragma unroll 1
+  for (int it = 0;; ++it) {
+    const bool have = cur.x < ntiles;
     if (have && cur_tma) { mbar_wait(s_bar, tma_parity); tma_parity ^= 1u; }
-    half_sync();                           // audio(tile) visible; P(previous tile) complete; E is free; s_ctl consumed
-    // the tile after this one is drawn now (one thread; the L2 prefetch of its box goes out with it) and published to the
-    // half through shared memory; it is read after the barrier that ends phase A
-    if (tid == STAGE_TID) s_ctl[1 + half] = have ? draw() : ntiles;
+    half_sync();                           // audio(tile) visible; P(previous tile) complete; E is free
 
     // ---- phase A: mel(previous tile) + pass 1(this tile) ----------------------------------------------
 #pragma unroll 1
@@ -291,13 +298,16 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
     half_sync();                           // E complete; the audio tile and P are dead from here on
 
     // ---- phase B: copy of the next tile (TMA, or plain stores at a clip edge) + pass 2(this tile) -------
-    const int next = s_ctl[1 + half];
-    cur_tma = (next < ntiles) ? stage(v_tile(wave, stride, lengths, next, use_tma)) : false;
+    // The tile after the next one is drawn here, by a thread of the warp that has no pass-2 task, into the ring slot
+    // this tile's descriptor occupied (last read one trip ago, two barriers back).
+    const int4 next = s_desc[(it + 1) & 1];
+    cur_tma = (next.x < ntiles) ? stage(unpack(next)) : false;
+    if (tid == STAGE_TID) s_desc[it & 1] = draw();
     if (p2_warp < 6) v_pass2(p2_k2, s_e + p2_col, s_p + p2_col);
     else if (p2_warp == 6 && lane < 16) v_pass2_real(s_e + p2_col, s_p + p2_col);
-    prev_clip = tile / V_TILES_PER_CLIP;
-    prev_f0 = (tile - prev_clip * V_TILES_PER_CLIP) * V_TILE;
-    tile = next;
+    prev_clip = cur.y;
+    prev_f0 = cur.z;
+    cur = next;
   }
 }
 
