@@ -53,13 +53,28 @@ def config1():
     dev = [wave[:, 0].cuda() * (1.0 - 0.01 * i) for i in range(4)]
     k = [0]
 
+    # 27 us of GPU work per call is below the host cost of an eager op call: replay one captured graph per input
+    for x in dev:
+        ops.mel_power(x, 1e-9)
+    torch.cuda.synchronize()
+    graphs, keep = [], []
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for x in dev:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                keep.append(ops.mel_power(x, 1e-9))
+            graphs.append(g)
+    torch.cuda.synchronize()
+
     def step():
-        ops.mel_power(dev[k[0] % 4], 1e-9)
+        graphs[k[0] % 4].replay()
         k[0] += 1
-    t = dev_time(step, 200)
+    t = dev_time(step, 400, warm=20)
     big = torch.randn(2048, 88200, device="cuda")
     tb = dev_time(lambda: ops.mel_power(big, 1e-9), 20)
     res = {"config": "1: urban 64-mel log-mel, 32 x 4 s clips", "gpu_s_per_batch": t, "gpu_clips_per_s": 32 / t,
+           "launch": "cuda graph replay of the public op, 4 rotating inputs",
            "gpu_clips_per_s_batch2048": 2048 / tb, "hbm_frac_batch2048": 2048 / tb * 397088 / PEAK}
     try:
         import torchaudio
