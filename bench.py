@@ -138,11 +138,23 @@ def make_reference_runner():
         return run, "port", f"oracle/logmel_oracle.py numpy port (transformers unavailable: {type(exc).__name__})"
 
 
+def use_all_host_threads() -> int:
+    """The CPU arms get every core this process may run on (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def run_reference(args) -> dict:
     import torch
     from audio_transformers_b200 import signals
     run, kind, desc = make_reference_runner()
-    cores = torch.get_num_threads()
+    cores = use_all_host_threads()
     pool = [[signals.whisper_clip(i, seed=p).astype(np.float64) for i in range(args.batch)] for p in range(2)]
     for w in range(args.warmup):
         run(pool[w % 2])
@@ -168,7 +180,8 @@ def cpu_baseline_leg(batch: int, budget_s: float = 12.0) -> dict:
     import torch
     from audio_transformers_b200 import signals
     run, kind, desc = make_reference_runner()
-    cores = torch.get_num_threads()
+    before = torch.get_num_threads()
+    cores = use_all_host_threads()
     clips = [signals.whisper_clip(i, seed=0).astype(np.float64) for i in range(min(batch, 16))]
     run(clips[:2])                                     # warm-up
     n, t0 = 0, time.perf_counter()
@@ -178,6 +191,7 @@ def cpu_baseline_leg(batch: int, budget_s: float = 12.0) -> dict:
         dt = time.perf_counter() - t0
         if dt > budget_s:
             break
+    torch.set_num_threads(before)
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{n} clips (30 s, 16 kHz) in {dt:.1f} s; {desc}; {cores} torch threads of {os.cpu_count()} cpus"}
 
