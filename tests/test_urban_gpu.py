@@ -129,3 +129,27 @@ def test_errors(ops):
         B200MelSpectrogram()(torch.zeros(1, 88200))
     with pytest.raises(ValueError):
         ops.mel_power(torch.zeros(1, 512, device="cuda"), 1e-9)
+
+
+@pytest.mark.parametrize("batch,n", [(37, 2048 + 17), (150, 1537), (5, 513), (64, 88200)])
+def test_flat_frame_list_straddles_clips(ops, batch, n):
+    """The packed kernel walks one flat list of frames: 32-frame tiles and frame pairs straddle clip boundaries at
+    every alignment (odd frame counts), clips shorter than a tile, many tiles per CTA."""
+    rng = np.random.default_rng(batch * 100003 + n)
+    wave = (0.3 * rng.standard_normal((batch, n))).astype(np.float32)
+    out = ops.mel_power(torch.from_numpy(wave).cuda(), 1e-9).cpu().numpy()
+    pick = sorted({0, 1, batch // 2, batch - 2, batch - 1})
+    ref = O.urban_melspec(wave[pick], dtype=np.float32)
+    assert out.shape == (batch, 64, 1 + n // 512)
+    assert np.abs(out[pick] - ref).max() <= TOL
+
+
+def test_large_batch_equals_single_clip_calls(ops):
+    """Size-independent property at a batch far above one tile per SM (600 clips = 3244 tiles on 148 CTAs): every clip's
+    features are bit-identical to the same clip processed alone, whatever tile / lane pair / CTA it lands in."""
+    g = torch.Generator().manual_seed(7)
+    wave = torch.randn(600, 88200, generator=g).cuda()
+    out = ops.mel_power(wave, 1e-9)
+    assert torch.isfinite(out).all()
+    for c in (0, 1, 172, 311, 598, 599):
+        assert torch.equal(out[c], ops.mel_power(wave[c:c + 1].contiguous(), 1e-9)[0]), c
