@@ -18,8 +18,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 
 #include "../../include/b200mel.h"
 
@@ -56,6 +60,71 @@ int fail_cuda(cudaError_t e, const char* where) {
   return B200MEL_ERR_CUDA;
 }
 
+}  // namespace
+
+// Persistent host worker pool for b200mel_host_pack: creating threads per call costs more than converting a 30 s
+// clip (measured: 0.33 ms on one thread, 0.68 ms when 7 fresh threads share the clip).  Workers sleep on a condition
+// variable between calls.  One job at a time (callers are serialised by a mutex); a process that forked after the
+// pool was built (DataLoader workers) gets a fresh pool, the inherited one has no threads behind it.
+namespace {
+class PackPool {
+ public:
+  static PackPool& get() {
+    static std::mutex guard;
+    static PackPool* inst = nullptr;
+    static pid_t owner = 0;
+    std::lock_guard<std::mutex> lk(guard);
+    if (!inst || owner != getpid()) { inst = new PackPool(); owner = getpid(); }   // the stale pool of the parent is leaked on purpose
+    return *inst;
+  }
+  // run fn(part), part = 0..parts-1, on the caller plus up to parts-1 workers; returns when all parts are done
+  void run(int parts, const std::function<void(int)>& fn) {
+    if (parts <= 1) { fn(0); return; }
+    std::lock_guard<std::mutex> job_lk(job_mutex_);
+    grow(parts - 1);
+    std::unique_lock<std::mutex> lk(m_);
+    fn_ = &fn; parts_ = parts; next_ = 0; pending_ = parts; ++generation_;
+    const unsigned long long mine = generation_;
+    cv_.notify_all();
+    drain(lk, mine);                                   // the caller works too, it does not just wait
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+ private:
+  void grow(int want) {
+    while ((int)workers_.size() < want && workers_.size() < 64) {
+      workers_.emplace_back([this] { loop(); });
+      workers_.back().detach();
+    }
+  }
+  // claim and run parts of job `gen` until none are left; called and returns with m_ held.  Parts are claimed under
+  // the lock, so a worker that is late can never run a part of a newer job with the older job's function.
+  void drain(std::unique_lock<std::mutex>& lk, unsigned long long gen) {
+    while (generation_ == gen && next_ < parts_) {
+      const int part = next_++;
+      const std::function<void(int)>* fn = fn_;
+      lk.unlock();
+      (*fn)(part);
+      lk.lock();
+      if (--pending_ == 0) done_cv_.notify_all();
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    std::unique_lock<std::mutex> lk(m_);
+    for (;;) {
+      cv_.wait(lk, [&] { return generation_ != seen; });
+      seen = generation_;
+      drain(lk, seen);
+    }
+  }
+  std::mutex job_mutex_, m_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, parts_ = 0, pending_ = 0;
+  unsigned long long generation_ = 0;
+};
 }  // namespace
 
 // cuTensorMapEncodeTiled, resolved through the runtime so that the library does not link libcuda directly
@@ -397,12 +466,11 @@ int b200mel_host_pack(const void* const* clips, const int64_t* lengths, int32_t 
     }
   };
   if (nt <= 1) { work(0, total); return B200MEL_OK; }
-  std::vector<std::thread> pool;
-  pool.reserve(nt - 1);
   const int64_t per = (total + nt - 1) / nt;
-  for (int t = 1; t < nt; ++t) pool.emplace_back(work, per * t, per * (t + 1) < total ? per * (t + 1) : total);
-  work(0, per < total ? per : total);
-  for (auto& th : pool) th.join();
+  PackPool::get().run(nt, [&](int part) {
+    const int64_t b = per * part, e = per * (part + 1) < total ? per * (part + 1) : total;
+    if (b < e) work(b, e);
+  });
   return B200MEL_OK;
 }
 

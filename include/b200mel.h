@@ -131,7 +131,8 @@ int b200mel_urban_prep_f32(b200mel_handle* h, const float* audio, int64_t in_str
  * ragged HOST clips (float32, or float64 when src_is_f64 != 0) into one row-major float32 HOST buffer `dst`
  * (`dst_stride` floats per row; pinned memory makes the following H2D copy asynchronous), converting and copying with
  * up to `threads` host threads.  Only min(lengths[i], max_samples) samples of a clip are copied; out_lengths (may be
- * NULL) receives those counts.  No CUDA calls. */
+ * NULL) receives those counts.  No CUDA calls.  The threads belong to a persistent pool inside the library (created on
+ * first use, re-created in a forked child); concurrent callers are serialised. */
 int b200mel_host_pack(const void* const* clips, const int64_t* lengths, int32_t n, int32_t src_is_f64,
                       int64_t max_samples, float* dst, int64_t dst_stride, int32_t* out_lengths, int32_t threads);
 

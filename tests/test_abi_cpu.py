@@ -105,3 +105,50 @@ def test_host_pack_matches_numpy_cast(lib):
     bad = lib.b200mel_host_pack(ptrs, lens.ctypes.data_as(ctypes.c_void_p), n, 0, 480000, dst.ctypes.data_as(ctypes.c_void_p),
                                 1000, None, 2)
     assert bad == -1 and b"longer than dst_stride" in lib.b200mel_last_error()
+
+
+def _pack_once(lib, clips, threads):
+    n = len(clips)
+    ptrs = (ctypes.c_void_p * n)(*[c.ctypes.data for c in clips])
+    lens = np.array([len(c) for c in clips], dtype=np.int64)
+    dst = np.full((n, 480000), 7.0, dtype=np.float32)
+    out = np.zeros(n, dtype=np.int32)
+    st = lib.b200mel_host_pack(ptrs, lens.ctypes.data_as(ctypes.c_void_p), n, 1, 480000, dst.ctypes.data_as(ctypes.c_void_p),
+                               480000, out.ctypes.data_as(ctypes.c_void_p), threads)
+    assert st == 0
+    for i, c in enumerate(clips):
+        L = min(len(c), 480000)
+        assert out[i] == L and np.array_equal(dst[i, :L], c[:L].astype(np.float32)) and (dst[i, L:] == 7.0).all()
+
+
+def test_host_pack_worker_pool(lib):
+    """The pack runs on a persistent worker pool: many calls with changing thread counts, concurrent callers from
+    several Python threads (ctypes drops the GIL), and a forked child (which must not wait on the parent's workers)."""
+    import threading
+    rng = np.random.default_rng(1)
+    clips = [rng.standard_normal(n) for n in (1, 159, 70000, 480000, 600000, 33333)]
+    for k in range(40):
+        _pack_once(lib, clips, 1 + (7 * k) % 16)
+    errors = []
+
+    def worker(seed):
+        try:
+            r = np.random.default_rng(seed)
+            for _ in range(20):
+                _pack_once(lib, clips, int(r.integers(1, 17)))
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors
+    pid = os.fork()
+    if pid == 0:                                  # child: the pool of the parent has no threads here
+        code = 1
+        try:
+            _pack_once(lib, clips, 8)
+            code = 0
+        finally:
+            os._exit(code)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
