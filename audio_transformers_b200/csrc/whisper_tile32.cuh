@@ -152,7 +152,7 @@ __device__ __forceinline__ void v_mel_filters(const float (&pb)[NB], float* __re
     float acc;
     v_mel_taps<0, w_mel_len(M), w_mel_off(M), w_mel_start(M) - BLO, NB>(pb, acc);
     const float e = fmaxf(acc, 1e-10f);
-    emax = fmaxf(emax, valid ? e : 0.0f);
+    emax = fmaxf(emax, e);                             // lanes past frame 3000 are masked once, in v_mel_phase
     const float y = w_norm_log(e);
     if (valid) out_col[(size_t)M * W_NFRAME] = y;
     v_mel_filters<M + 1, FE, BLO, NB>(pb, out_col, valid, emax);
@@ -183,6 +183,7 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
 #define V_MEL_CASE(w) case w: v_mel_share<2 * w, 16>(pl, out_col, valid, emax); v_mel_share<2 * w + 1, 16>(pl, out_col, valid, emax); break;
   switch (warp) { V_MEL_CASE(0) V_MEL_CASE(1) V_MEL_CASE(2) V_MEL_CASE(3) V_MEL_CASE(4) V_MEL_CASE(5) V_MEL_CASE(6) default: V_MEL_CASE(7) }
 #undef V_MEL_CASE
+  if (!valid) emax = 0.0f;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   if (lane == 0) *v_slot(tile_max, clip, f0, warp) = emax;
