@@ -35,7 +35,7 @@ whisper_clamp_kernel32(float* __restrict__ out, const float* __restrict__ tile_m
   constexpr int VEC_PER_PART = W_NMEL * W_NFRAME / 4 / CL_PARTS;       // 3750
   constexpr int VEC_PER_ROW = W_NFRAME / 4;                            // 750
   const int tid = threadIdx.x;
-  const float y_silent = w_norm_log(1e-10f);
+  const float y_silent = v_norm_log(V_EFLOOR);
   for (int item = blockIdx.x; item < batch * CL_PARTS; item += gridDim.x) {
     const int clip = item / CL_PARTS, part = item - clip * CL_PARTS;
     float m = 0.0f;
@@ -47,7 +47,7 @@ whisper_clamp_kernel32(float* __restrict__ out, const float* __restrict__ tile_m
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < CL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
-    const float thr = w_norm_log(m) - 2.0f;
+    const float thr = v_norm_log(m) - 2.0f;                // slots hold energies scaled by V_ESCALE
     // frames from `fs` on belong to tiles of pure zero padding, which the log-mel kernel did not write: their value is
     // known without reading (the silent tiles are a suffix of the clip: v_tile_silent is monotone in f0)
     const long long len_ll = lengths ? (long long)lengths[clip] : stride;

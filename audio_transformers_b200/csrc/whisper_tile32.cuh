@@ -54,6 +54,17 @@ __device__ __forceinline__ WTile v_tile(const float* __restrict__ wave, long lon
   return t;
 }
 
+// The 32-frame kernel carries its mel energies scaled by 1e4 (the scale is folded into the filter weights, which are
+// immediates): (log10(e) + 4) / 4 = log10(1e4 e) / 4 is then a single multiply after lg2, with no "+ 1" whose
+// constant the compiler re-materialised with a MOV for every value.  The workspace slots and the floor pass use the
+// same scaled unit (V_EFLOOR is the reference's 1e-10 clamp).
+constexpr float V_ESCALE = 1e4f, V_EFLOOR = 1e-10f * V_ESCALE;
+__device__ __forceinline__ float v_norm_log(float e_scaled) {
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(e_scaled));
+  return l * 0.07525749891599529f;
+}
+
 // Workspace of this kernel: one float per (clip, tile, warp) = the largest mel energy that warp saw in that tile.
 // Every slot is written exactly once per launch, so the workspace needs no zeroing (no memset node, no atomics),
 // and the clip-floor pass reduces a clip's 94 x 8 slots itself.
@@ -66,7 +77,7 @@ __device__ __forceinline__ float* v_slot(float* __restrict__ tile_max, int clip,
 // max(., 1e-10)) is recorded so that an all-silent clip still has a defined clip maximum.  Called by ONE thread.
 __device__ __forceinline__ void v_record_silent(const WTile& t, float* __restrict__ tile_max) {
 #pragma unroll
-  for (int w = 0; w < V_WARPS; ++w) *v_slot(tile_max, t.clip, t.f0, w) = 1e-10f;
+  for (int w = 0; w < V_WARPS; ++w) *v_slot(tile_max, t.clip, t.f0, w) = V_EFLOOR;
 }
 
 __device__ __forceinline__ void v_stage_generic(const WTile& t, float* __restrict__ s_audio, int part, int nparts, int lane) {
@@ -140,7 +151,7 @@ __device__ __forceinline__ void v_pass2_real(const float2* __restrict__ e_col, f
 template <int J, int LEN, int OFF, int REL, int NB>
 __device__ __forceinline__ void v_mel_taps(const float (&pb)[NB], float& acc) {
   if constexpr (J < LEN) {
-    constexpr float wt = w_mel_wt(OFF + J);
+    constexpr float wt = w_mel_wt(OFF + J) * V_ESCALE;
     acc = (J == 0) ? pb[REL + J] * wt : __fmaf_rn(pb[REL + J], wt, acc);
     v_mel_taps<J + 1, LEN, OFF, REL, NB>(pb, acc);
   }
@@ -151,9 +162,9 @@ __device__ __forceinline__ void v_mel_filters(const float (&pb)[NB], float* __re
   if constexpr (M < FE) {
     float acc;
     v_mel_taps<0, w_mel_len(M), w_mel_off(M), w_mel_start(M) - BLO, NB>(pb, acc);
-    const float e = fmaxf(acc, 1e-10f);
+    const float e = fmaxf(acc, V_EFLOOR);
     emax = fmaxf(emax, e);                             // lanes past frame 3000 are masked once, in v_mel_phase
-    const float y = w_norm_log(e);
+    const float y = v_norm_log(e);
     if (valid) out_col[(size_t)M * W_NFRAME] = y;
     v_mel_filters<M + 1, FE, BLO, NB>(pb, out_col, valid, emax);
   }
