@@ -47,7 +47,8 @@ whisper_clamp_kernel32(float* __restrict__ out, const float* __restrict__ tile_m
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < CL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
-    const float thr = v_norm_log(m) - 2.0f;                // slots hold energies scaled by V_ESCALE
+    // slots hold energies scaled by V_ESCALE; the log-mel kernel leaves the reference's clamp at 1e-10 to this pass
+    const float thr = fmaxf(v_norm_log(m) - 2.0f, y_silent);
     // frames from `fs` on belong to tiles of pure zero padding, which the log-mel kernel did not write: their value is
     // known without reading (the silent tiles are a suffix of the clip: v_tile_silent is monotone in f0)
     const long long len_ll = lengths ? (long long)lengths[clip] : stride;

@@ -162,9 +162,10 @@ __device__ __forceinline__ void v_mel_filters(const float (&pb)[NB], float* __re
   if constexpr (M < FE) {
     float acc;
     v_mel_taps<0, w_mel_len(M), w_mel_off(M), w_mel_start(M) - BLO, NB>(pb, acc);
-    const float e = fmaxf(acc, V_EFLOOR);
-    emax = fmaxf(emax, e);                             // lanes past frame 3000 are masked once, in v_mel_phase
-    const float y = v_norm_log(e);
+    // No clamp at the reference's 1e-10 floor here: the floor pass raises every value to max(clip max - 8 decades,
+    // floor) anyway (an exact zero gives -inf for the moment).  Lanes past frame 3000 are masked once, in v_mel_phase.
+    emax = fmaxf(emax, acc);
+    const float y = v_norm_log(acc);
     if (valid) out_col[(size_t)M * W_NFRAME] = y;
     v_mel_filters<M + 1, FE, BLO, NB>(pb, out_col, valid, emax);
   }
