@@ -196,8 +196,8 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
   switch (warp) { V_MEL_CASE(0) V_MEL_CASE(1) V_MEL_CASE(2) V_MEL_CASE(3) V_MEL_CASE(4) V_MEL_CASE(5) V_MEL_CASE(6) default: V_MEL_CASE(7) }
 #undef V_MEL_CASE
   if (!valid) emax = 0.0f;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  // energies are >= +0, so their bit patterns order like the values: one REDUX instead of five shuffle/max rounds
+  emax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(emax)));
   if (lane == 0) *v_slot(tile_max, clip, f0, warp) = emax;
 }
 
