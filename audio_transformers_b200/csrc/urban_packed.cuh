@@ -131,16 +131,21 @@ __device__ __forceinline__ void u2_pass2(int k2, int h, int q, const float* __re
   const float2* __restrict__ e2 = reinterpret_cast<const float2*>(s_e) + (2 * k2) * 16 + q;     // + r * (U2_EP / 2); Im = +16
   const float4* __restrict__ t4 = reinterpret_cast<const float4*>(s_img + U2_IMG_T4) + (k2 * 32) * 2 + h;   // + r * 2
   float2 ur[16], ui[16], Xr[16], Xi[16];
+  // T_h[k2][r + 16] = T_h[k2][r] * C with C = T_h[k2][16] (T_h[k2][0] = 1), so u = T[r] (Y_r + C Y_{r+16}): the same
+  // eight packed operations per r with one table load instead of two
+  const float4 tc = t4[16 * 2];
+  const float2 cc = make_float2(tc.x, tc.y), cs = make_float2(tc.z, tc.w);
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const float2 ar = e2[r * (U2_EP / 2)], ai = e2[r * (U2_EP / 2) + 16];
     const float2 br = e2[(r + 16) * (U2_EP / 2)], bi = e2[(r + 16) * (U2_EP / 2) + 16];
-    const float4 ta = t4[r * 2], tb = t4[(r + 16) * 2];
+    const float4 ta = t4[r * 2];
     const float2 ac = make_float2(ta.x, ta.y), as = make_float2(ta.z, ta.w);
-    const float2 bc = make_float2(tb.x, tb.y), bs = make_float2(tb.z, tb.w);
     // (yr + i yi)(c - i s) = (yr c + yi s) + i (yi c - yr s)
-    ur[r] = b2::vfma(ar, ac, b2::vfma(ai, as, b2::vfma(br, bc, b2::vmul(bi, bs))));
-    ui[r] = b2::vfma(ai, ac, b2::vfma(b2::vneg(ar), as, b2::vfma(bi, bc, b2::vmul(b2::vneg(br), bs))));
+    const float2 tr = b2::vfma(br, cc, b2::vfma(bi, cs, ar));
+    const float2 ti = b2::vfma(bi, cc, b2::vfma(b2::vneg(br), cs, ai));
+    ur[r] = b2::vfma(tr, ac, b2::vmul(ti, as));
+    ui[r] = b2::vfma(ti, ac, b2::vmul(b2::vneg(tr), as));
   }
   b2::cplx_dft16(ur, ui, Xr, Xi);
   float2* __restrict__ p2 = reinterpret_cast<float2*>(s_p) + q;
