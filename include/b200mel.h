@@ -104,6 +104,7 @@ int b200mel_whisper_frame_mask(b200mel_handle* h, const int32_t* lengths, int32_
  *             reflect padding needs it), stride_samples % 4 == 0.
  *   log_eps   >= 0: out = log(mel + log_eps) (natural log; the reference uses 1e-9);  < 0: out = mel.
  *   out       [batch][64][1 + n_samples/512] float32.
+ * batch * (1 + n_samples/512) must stay below 2^31 - 256 (the kernel walks one flat list of frames).
  */
 int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples, int32_t n_samples,
                     int32_t batch, float log_eps, float* out, void* stream);
