@@ -22,6 +22,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <utility>
 #include <vector>
 #include <unistd.h>
 
@@ -35,6 +36,11 @@ namespace host_tab {                      // host copies, so table queries need 
 #include "generated/tables.inc"
 #undef B200MEL_CONST
 }  // namespace host_tab
+namespace dev_tab {                       // global-memory copies, for tables a kernel indexes per lane
+#define B200MEL_CONST static __device__ const
+#include "generated/tables.inc"
+#undef B200MEL_CONST
+}  // namespace dev_tab
 #include "fft_codelets.cuh"
 
 namespace {
@@ -43,6 +49,7 @@ namespace {
 #include "whisper_tile64.cuh"
 #include "whisper_tile32.cuh"
 #include "whisper_post.cuh"
+#include "whisper_pipe.cuh"
 #include "urban.cuh"
 #include "urban_packed.cuh"
 
@@ -137,6 +144,7 @@ struct b200mel_handle {
   int preset;
   int sm_count;
   tmap_encode_fn encode = nullptr;   // Whisper preset: TMA descriptor encoder
+  const float* win400 = nullptr;     // Whisper preset: device address of the window table (global memory)
   float* uimg = nullptr;             // urban preset: table image of the packed kernel (device)
   // optional benchmark instrumentation (b200mel_profile_begin/end)
   bool prof_on = false;
@@ -176,6 +184,10 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(whisper_logmel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(whisper_logmel_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xp::X_SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(whisper_logmel_pipe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess)
     e = cudaFuncSetAttribute(urban_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(urban_mel_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES);
@@ -193,6 +205,12 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
       cudaSetDevice(prev);
       return fail_cuda(e, "b200mel_create: table upload");
     }
+  }
+  if (preset == B200MEL_PRESET_WHISPER) {
+    void* sym = nullptr;
+    e = cudaGetSymbolAddress(&sym, dev_tab::c_win400);
+    if (e != cudaSuccess) { delete h; cudaSetDevice(prev); return fail_cuda(e, "cudaGetSymbolAddress"); }
+    h->win400 = (const float*)sym;
   }
   cudaSetDevice(prev);
   if (preset == B200MEL_PRESET_WHISPER) {
@@ -254,8 +272,13 @@ int b200mel_profile_end(b200mel_handle* h, double* total_ms, int32_t* launches) 
 size_t b200mel_workspace_bytes(const b200mel_handle* h, int32_t batch) {
   if (!h || batch <= 0) return 0;
   if (h->preset != B200MEL_PRESET_WHISPER) return 0;
-  // 32-frame kernel: one float per (clip, tile, warp); 64-frame kernel: one word per clip
-  return ((size_t)batch * V_SLOTS_PER_CLIP * sizeof(float) + 255) & ~(size_t)255;
+  // one 64-bit word per clip plus the CTA counter (whisper_pipe.cuh); the legacy kernels want a float per (clip, tile, warp)
+  size_t need = ((size_t)batch + 2 + 8 * 2 * 160) * sizeof(unsigned long long);   // + development counters
+#ifdef B200MEL_LEGACY_KERNELS
+  const size_t old = (size_t)batch * V_SLOTS_PER_CLIP * sizeof(float);
+  need = need > old ? need : old;
+#endif
+  return (need + 255) & ~(size_t)255;
 }
 
 int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples,
@@ -272,6 +295,32 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
     return fail(B200MEL_ERR_WORKSPACE, "whisper_logmel: workspace too small (see b200mel_workspace_bytes)");
   if ((long long)batch * V_TILES_PER_CLIP > 0x7fffffffLL) return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel: batch too large for one launch");
   cudaStream_t stream = (cudaStream_t)stream_;
+  static const bool legacy = getenv("B200MEL_KERNEL32") != nullptr || getenv("B200MEL_KERNEL64") != nullptr;
+  if (!legacy) {
+    // one persistent warp-specialised CTA per SM; the clip floor is applied inside the same kernel
+    const long long nt = (long long)batch * xp::X_TILES_PER_CLIP;
+    const int grid = nt < (long long)h->sm_count ? (int)nt : h->sm_count;
+    xp::XArgs args;
+    args.wave = wave; args.stride = (long long)stride_samples; args.lengths = lengths; args.batch = batch;
+    args.out = out; args.ws = (unsigned long long*)workspace; args.win400 = h->win400;
+    { static const char* dbg = getenv("B200MEL_PIPE_DEBUG"); args.debug = dbg ? atoi(dbg) : 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(xp::X_THREADS);
+    cfg.dynamicSmemBytes = xp::X_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    { static const bool no_pdl = getenv("B200MEL_NO_PDL") != nullptr; cfg.numAttrs = no_pdl ? 0 : 1; }
+    const bool prof = h->prof_on && h->prof_n < h->prof_cap;
+    if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, whisper_logmel_pipe_kernel, args);
+    if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
+    if (le != cudaSuccess) return fail_cuda(le, "whisper_logmel_pipe_kernel launch");
+    return B200MEL_OK;
+  }
   const bool k32 = getenv("B200MEL_KERNEL64") == nullptr;        // default: 32-frame tiles, two CTAs per SM
   unsigned int* clip_max = (unsigned int*)workspace;
   cudaError_t e = cudaSuccess;

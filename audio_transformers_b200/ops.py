@@ -24,7 +24,6 @@ U_NMEL, U_HOP, U_NFFT = 64, 512, 1024
 
 _handles: dict = {}
 _hlock = threading.Lock()
-_ws_bytes: dict = {}          # (device index, batch) -> workspace size
 
 
 def _handle(device: torch.device, preset: int) -> ctypes.c_void_p:
@@ -59,12 +58,42 @@ _LIBDEF.define("urban_prep(Tensor audio, Tensor? lengths, int orig_freq, int new
                "int out_samples) -> Tensor")
 
 
+_workspaces: dict = {}        # (device index, stream, batch) -> zero-initialised workspace tensor
+
+
+def _whisper_workspace(lib, h, dev: torch.device, stream: int, batch: int) -> torch.Tensor:
+    """The kernel's per-clip control words.  They must be zero before the first launch and every launch leaves them
+    zero again (include/b200mel.h), so one buffer per (device, stream, batch) is zeroed once and reused; calls on
+    different streams never share one."""
+    key = (dev.index, stream, batch)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = max(int(lib.b200mel_workspace_bytes(h, batch)), 16)
+        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+        if not torch.cuda.is_current_stream_capturing():
+            if len(_workspaces) > 256:
+                _workspaces.clear()
+            _workspaces[key] = ws
+    return ws
+
+
 def _whisper_logmel_cuda(wave: torch.Tensor, lengths: Optional[torch.Tensor]) -> torch.Tensor:
     _require_cuda(wave, "wave")
     if wave.dim() != 2 or wave.dtype != torch.float32:
         raise ValueError("b200mel.whisper_logmel: wave must be a (B, T) float32 tensor")
     batch, t = wave.shape
-    if t % 4 != 0 or wave.stride(1) != 1 or wave.stride(0) % 4 != 0 or wave.data_ptr() % 16 != 0:
+    if lengths is not None:
+        _require_cuda(lengths, "lengths")
+        if lengths.device != wave.device:
+            raise ValueError("b200mel.whisper_logmel: lengths must live on the same device as wave")
+        if lengths.numel() != batch:
+            raise ValueError("b200mel.whisper_logmel: lengths must have one entry per clip")
+        if lengths.dtype != torch.int32:
+            lengths = lengths.to(torch.int32)
+        # a clip never extends past its row of the (B, T) view (stream-ordered, no host sync)
+        lengths = lengths.clamp(max=t).contiguous()
+    if t % 4 != 0 or wave.stride(1) != 1 or wave.stride(0) % 4 != 0 or wave.data_ptr() % 16 != 0 or \
+            (batch > 1 and wave.stride(0) < t):
         # keep the kernel's alignment contract: repack into a 16-byte aligned, stride%4==0 buffer
         tp = (t + 3) // 4 * 4
         if lengths is None:
@@ -73,28 +102,21 @@ def _whisper_logmel_cuda(wave: torch.Tensor, lengths: Optional[torch.Tensor]) ->
         buf[:, :t] = wave
         wave = buf
     stride = wave.stride(0) if batch > 1 else wave.shape[1]
-    if lengths is not None:
-        _require_cuda(lengths, "lengths")
-        if lengths.dtype != torch.int32:
-            lengths = lengths.to(torch.int32)
-        lengths = lengths.contiguous()
-        if lengths.numel() != batch:
-            raise ValueError("b200mel.whisper_logmel: lengths must have one entry per clip")
+    if lengths is None and stride != t:
+        # a column-sliced view: without lengths the C ABI takes the whole row stride as the clip
+        lengths = torch.full((batch,), t, dtype=torch.int32, device=wave.device)
     out = torch.empty((batch, W_NMEL, W_NFRAME), dtype=torch.float32, device=wave.device)
     if batch == 0:
         return out
     lib = _lib.load()
     dev = wave.device
     h = _handle(dev, _lib.PRESET_WHISPER)
-    key = (dev.index, batch)
-    ws_bytes = _ws_bytes.get(key)
-    if ws_bytes is None:
-        ws_bytes = _ws_bytes[key] = max(int(lib.b200mel_workspace_bytes(h, batch)), 16)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    # the host side of a call is ~50 us of Python; a 64-clip step is ~85 us on the GPU, so keep this path lean: no
-    # device context manager unless the tensor lives on another device than the current one
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = _whisper_workspace(lib, h, dev, stream, batch)
+    # the host side of a call is a few tens of microseconds of Python against ~60 us on the GPU for 64 clips, so keep
+    # this path lean: no device context manager unless the tensor lives on another device than the current one
     args = (h, wave.data_ptr(), stride, lengths.data_ptr() if lengths is not None else None, batch, out.data_ptr(),
-            ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
+            ws.data_ptr(), ws.numel(), stream)
     if dev.index == torch.cuda.current_device():
         st = lib.b200mel_whisper_logmel_f32(*args)
     else:
