@@ -26,11 +26,27 @@ def nvcc_path() -> str:
     return p
 
 
+STAMP = OUT + ".sources.sha256"
+
+
+def sources_digest() -> str:
+    """sha256 over the flags and every source the library is built from (names and bytes)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in DEPS:
+        h.update(os.path.relpath(d, HERE).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def up_to_date() -> bool:
-    if not os.path.exists(OUT):
+    """True when the library on disk was built from exactly the present sources (a content hash written next to it:
+    modification times say nothing about a snapshot that was copied to another box)."""
+    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(d) <= t for d in DEPS if os.path.exists(d))
+    with open(STAMP) as f:
+        return f.read().strip() == sources_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -42,6 +58,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed ({res.returncode}): {' '.join(cmd)}")
+    with open(STAMP, "w") as f:
+        f.write(sources_digest() + "\n")
     return OUT
 
 

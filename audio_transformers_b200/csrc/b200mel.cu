@@ -4,11 +4,10 @@
 // HF:feature_extraction_sequence_utils.py:263-278,327-332): one fused persistent kernel turns float32 audio into
 // normalised log-mel -- TMA-staged audio tiles, two-pass prime-factor real FFT (25 x 16) on packed f32x2 frame
 // pairs, |X|^2, sparse mel projection, log, per-clip max -- followed by a small in-place pass that applies the
-// clip-wide floor.  whisper_common.cuh holds the building blocks, whisper_tile32.cuh the default kernel (32-frame
-// tiles, two CTAs per SM), whisper_tile64.cuh the 64-frame variant, whisper_post.cuh the floor / mask kernels.
-// Urban preset (urban.cuh): fused 1024-point mel kernel and the pre-step kernels (resample, peak normalisation).
-//
-// Nothing but the audio (read once) and the features touches HBM.  DESIGN.md has the layouts and the measurements.
+// clip-wide floor (it re-reads the features once, from L2 at the reference's batch sizes).  whisper_common.cuh holds
+// geometry and primitives, whisper_tile32.cuh the kernel (32-frame tiles, two independent halves per SM),
+// whisper_post.cuh the floor / mask kernels.  Urban preset: urban_packed.cuh (fused 1024-point mel kernel) and
+// urban.cuh (the pre-step kernels: mono mix, resample, peak normalisation).  DESIGN.md has the layouts and the measurements.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,12 +16,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
 #include <thread>
-#include <utility>
 #include <vector>
 #include <unistd.h>
 
@@ -36,20 +35,13 @@ namespace host_tab {                      // host copies, so table queries need 
 #include "generated/tables.inc"
 #undef B200MEL_CONST
 }  // namespace host_tab
-namespace dev_tab {                       // global-memory copies, for tables a kernel indexes per lane
-#define B200MEL_CONST static __device__ const
-#include "generated/tables.inc"
-#undef B200MEL_CONST
-}  // namespace dev_tab
 #include "fft_codelets.cuh"
 
 namespace {
 
 #include "whisper_common.cuh"
-#include "whisper_tile64.cuh"
 #include "whisper_tile32.cuh"
 #include "whisper_post.cuh"
-#include "whisper_pipe.cuh"
 #include "urban.cuh"
 #include "urban_packed.cuh"
 
@@ -144,8 +136,8 @@ struct b200mel_handle {
   int preset;
   int sm_count;
   tmap_encode_fn encode = nullptr;   // Whisper preset: TMA descriptor encoder
-  const float* win400 = nullptr;     // Whisper preset: device address of the window table (global memory)
   float* uimg = nullptr;             // urban preset: table image of the packed kernel (device)
+  bool no_tma = false;               // test hook (B200MEL_DEBUG_NO_TMA=1 at create time): every audio tile takes the ordinary-store path
   // optional benchmark instrumentation (b200mel_profile_begin/end)
   bool prof_on = false;
   int prof_cap = 0, prof_n = 0;
@@ -176,19 +168,9 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
   cudaGetDevice(&prev);
   e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
-  e = cudaFuncSetAttribute(whisper_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(whisper_logmel_kernel32, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES);
+  e = cudaFuncSetAttribute(whisper_logmel_kernel32, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(whisper_logmel_kernel32, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(whisper_logmel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(whisper_logmel_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xp::X_SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(whisper_logmel_pipe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(urban_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(urban_mel_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES);
   if (e != cudaSuccess) { cudaSetDevice(prev); return fail_cuda(e, "cudaFuncSetAttribute"); }
@@ -206,12 +188,6 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
       return fail_cuda(e, "b200mel_create: table upload");
     }
   }
-  if (preset == B200MEL_PRESET_WHISPER) {
-    void* sym = nullptr;
-    e = cudaGetSymbolAddress(&sym, dev_tab::c_win400);
-    if (e != cudaSuccess) { delete h; cudaSetDevice(prev); return fail_cuda(e, "cudaGetSymbolAddress"); }
-    h->win400 = (const float*)sym;
-  }
   cudaSetDevice(prev);
   if (preset == B200MEL_PRESET_WHISPER) {
     void* fn = nullptr;
@@ -222,6 +198,7 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
       return fail(B200MEL_ERR_CUDA, "b200mel_create: cuTensorMapEncodeTiled is not available from this driver");
     }
     h->encode = (tmap_encode_fn)fn;
+    h->no_tma = getenv("B200MEL_DEBUG_NO_TMA") != nullptr;
   }
   *out = h;
   return B200MEL_OK;
@@ -272,13 +249,8 @@ int b200mel_profile_end(b200mel_handle* h, double* total_ms, int32_t* launches) 
 size_t b200mel_workspace_bytes(const b200mel_handle* h, int32_t batch) {
   if (!h || batch <= 0) return 0;
   if (h->preset != B200MEL_PRESET_WHISPER) return 0;
-  // one 64-bit word per clip plus the CTA counter (whisper_pipe.cuh); the legacy kernels want a float per (clip, tile, warp)
-  size_t need = ((size_t)batch + 2 + 8 * 2 * 160) * sizeof(unsigned long long);   // + development counters
-#ifdef B200MEL_LEGACY_KERNELS
-  const size_t old = (size_t)batch * V_SLOTS_PER_CLIP * sizeof(float);
-  need = need > old ? need : old;
-#endif
-  return (need + 255) & ~(size_t)255;
+  // 32-frame kernel: one float per (clip, tile, warp); 64-frame kernel: one word per clip
+  return ((size_t)batch * V_SLOTS_PER_CLIP * sizeof(float) + 255) & ~(size_t)255;
 }
 
 int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples,
@@ -295,39 +267,6 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
     return fail(B200MEL_ERR_WORKSPACE, "whisper_logmel: workspace too small (see b200mel_workspace_bytes)");
   if ((long long)batch * V_TILES_PER_CLIP > 0x7fffffffLL) return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel: batch too large for one launch");
   cudaStream_t stream = (cudaStream_t)stream_;
-  static const bool legacy = getenv("B200MEL_KERNEL32") != nullptr || getenv("B200MEL_KERNEL64") != nullptr;
-  if (!legacy) {
-    // one persistent warp-specialised CTA per SM; the clip floor is applied inside the same kernel
-    const long long nt = (long long)batch * xp::X_TILES_PER_CLIP;
-    const int grid = nt < (long long)h->sm_count ? (int)nt : h->sm_count;
-    xp::XArgs args;
-    args.wave = wave; args.stride = (long long)stride_samples; args.lengths = lengths; args.batch = batch;
-    args.out = out; args.ws = (unsigned long long*)workspace; args.win400 = h->win400;
-    { static const char* dbg = getenv("B200MEL_PIPE_DEBUG"); args.debug = dbg ? atoi(dbg) : 0; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(xp::X_THREADS);
-    cfg.dynamicSmemBytes = xp::X_SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    { static const bool no_pdl = getenv("B200MEL_NO_PDL") != nullptr; cfg.numAttrs = no_pdl ? 0 : 1; }
-    const bool prof = h->prof_on && h->prof_n < h->prof_cap;
-    if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
-    cudaError_t le = cudaLaunchKernelEx(&cfg, whisper_logmel_pipe_kernel, args);
-    if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
-    if (le != cudaSuccess) return fail_cuda(le, "whisper_logmel_pipe_kernel launch");
-    return B200MEL_OK;
-  }
-  const bool k32 = getenv("B200MEL_KERNEL64") == nullptr;        // default: 32-frame tiles, two CTAs per SM
-  unsigned int* clip_max = (unsigned int*)workspace;
-  cudaError_t e = cudaSuccess;
-  if (!k32) {
-    e = cudaMemsetAsync(clip_max, 0, (size_t)batch * sizeof(unsigned int), stream);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
-  }
   // TMA view of the audio: [clip][y][x], element (x, y, clip) = wave[clip * stride + 160 y + x], x < 284.  Rows
   // overlap (y-stride 160 samples < 284), which is what lets a box start at any sample with 16-byte aligned
   // strides.  NY is chosen so that every in-bounds element lies inside its clip's row of the buffer.
@@ -337,54 +276,40 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   if (stride_samples >= W_TMAP_X) {
     const cuuint64_t dims[3] = {(cuuint64_t)W_TMAP_X, (cuuint64_t)((stride_samples - W_TMAP_X) / W_HOP + 1), (cuuint64_t)batch};
     const cuuint64_t strides[2] = {(cuuint64_t)W_HOP * sizeof(float), (cuuint64_t)stride_samples * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)W_PITCH, (cuuint32_t)(k32 ? V_ROWS : W_ROWS), 1};
+    const cuuint32_t box[3] = {(cuuint32_t)W_PITCH, (cuuint32_t)V_ROWS, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = h->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)wave, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(B200MEL_ERR_CUDA, "whisper_logmel: cuTensorMapEncodeTiled failed");
-    use_tma = getenv("B200MEL_DEBUG_NO_TMA") ? 0 : 1;   // debug knob: every tile through the generic staging path
+    use_tma = h->no_tma ? 0 : 1;
   }
-  const int ntiles = batch * W_TILES_PER_CLIP;
-  const int grid_main = ntiles < h->sm_count ? ntiles : h->sm_count;   // persistent: one 512-thread CTA per SM
   const bool prof = h->prof_on && h->prof_n < h->prof_cap;
   if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
-  if (k32) {
-    const long long nt = (long long)batch * V_TILES_PER_CLIP;
-    const int grid32 = nt < (long long)h->sm_count ? (int)nt : h->sm_count;     // one 512-thread CTA (two halves) per SM
-    // programmatic stream serialisation: the kernel may begin while the previous kernel of the stream is finishing
-    // (it waits with griddepcontrol.wait before its first global write); with profiling on the event records sit
-    // between the kernels and switch the overlap off
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid32);
-    cfg.blockDim = dim3(V_THREADS);
-    cfg.dynamicSmemBytes = V_SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, whisper_logmel_kernel32, tmap, use_tma, wave, (long long)stride_samples, lengths, (int)batch, out,
-                           (float*)workspace);
-    if (e != cudaSuccess) return fail_cuda(e, "whisper_logmel_kernel32 launch");
-  } else {
-    whisper_logmel_kernel<<<grid_main, W_THREADS, W_SMEM_BYTES, stream>>>(
-        tmap, use_tma, wave, (long long)stride_samples, lengths, batch, out, clip_max);
-  }
+  const long long nt = (long long)batch * V_TILES_PER_CLIP;
+  const int grid32 = nt < (long long)h->sm_count ? (int)nt : h->sm_count;     // one 512-thread CTA (two halves) per SM
+  // programmatic stream serialisation: the kernel may become resident while the previous kernel of the stream is
+  // finishing (it waits with griddepcontrol.wait before its first global access); with profiling on the event records
+  // sit between the kernels and switch the overlap off
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid32);
+  cfg.blockDim = dim3(V_THREADS);
+  cfg.dynamicSmemBytes = V_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, whisper_logmel_kernel32, tmap, use_tma, wave, (long long)stride_samples, lengths,
+                                     (int)batch, out, (float*)workspace);
+  if (e != cudaSuccess) return fail_cuda(e, "whisper_logmel_kernel32 launch");
   if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
+  const int items = batch * CL_PARTS;
+  const int grid = items < CL_CTAS_PER_SM * h->sm_count ? items : CL_CTAS_PER_SM * h->sm_count;
+  whisper_clamp_kernel32<<<grid, CL_THREADS, 0, stream>>>(out, (const float*)workspace, batch, lengths, (long long)stride_samples);
   e = cudaGetLastError();
-  if (e != cudaSuccess) return fail_cuda(e, "whisper_logmel_kernel launch");
-  if (k32) {
-    const int items = batch * CL_PARTS;
-    const int grid = items < CL_CTAS_PER_SM * h->sm_count ? items : CL_CTAS_PER_SM * h->sm_count;
-    whisper_clamp_kernel32<<<grid, CL_THREADS, 0, stream>>>(out, (const float*)workspace, batch, lengths, (long long)stride_samples);
-  } else {
-    dim3 grid(30, batch);
-    whisper_clamp_kernel<<<grid, 256, 0, stream>>>(out, clip_max, batch);
-  }
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return fail_cuda(e, "whisper_clamp_kernel launch");
+  if (e != cudaSuccess) return fail_cuda(e, "whisper_clamp_kernel32 launch");
   return B200MEL_OK;
 }
 
@@ -394,6 +319,7 @@ int b200mel_whisper_frame_mask(b200mel_handle* h, const int32_t* lengths, int32_
   if (batch < 0) return fail(B200MEL_ERR_BAD_ARG, "frame_mask: negative batch");
   if (batch == 0) return B200MEL_OK;
   if (!lengths || !mask_out) return fail(B200MEL_ERR_BAD_ARG, "frame_mask: NULL lengths/mask_out");
+  if (batch > 0x7fffffff / W_NFRAME) return fail(B200MEL_ERR_BAD_ARG, "frame_mask: batch too large for one launch");
   const int n = batch * W_NFRAME;
   whisper_frame_mask_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(lengths, batch, mask_out);
   cudaError_t e = cudaGetLastError();
@@ -411,25 +337,17 @@ int b200mel_mel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples
   if (stride_samples < n_samples || (stride_samples & 3)) return fail(B200MEL_ERR_BAD_ARG, "mel: stride_samples must be >= n_samples and a multiple of 4");
   if (((uintptr_t)wave & 15) || ((uintptr_t)out & 3)) return fail(B200MEL_ERR_BAD_ALIGN, "mel: wave must be 16-byte aligned");
   const int n_frames = 1 + n_samples / U_HOP;
-  const int tiles_per_clip = (n_frames + U_TILE - 1) / U_TILE;
-  if ((long long)batch * tiles_per_clip > 0x7fffffffLL) return fail(B200MEL_ERR_BAD_ARG, "mel: batch too large for one launch");
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool prof = h->prof_on && h->prof_n < h->prof_cap;
   if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], stream);
-  static const bool v1 = getenv("B200MEL_URBAN_V1") != nullptr;     // first kernel, kept for A/B runs
-  if (v1) {
-    urban_mel_kernel<<<batch * tiles_per_clip, U_THREADS, U_SMEM_BYTES, stream>>>(
-        wave, (long long)stride_samples, n_samples, n_frames, tiles_per_clip, batch, log_eps, out);
-  } else {
-    const long long total_frames = (long long)batch * n_frames;
-    if (total_frames > 0x7fffff00LL) return fail(B200MEL_ERR_BAD_ARG, "mel: batch * frames must fit 31 bits");
-    const int n_tiles = (int)((total_frames + 31) / 32);
-    urban_mel_packed_kernel<<<n_tiles < h->sm_count ? n_tiles : h->sm_count, U2_THREADS, U2_SMEM_BYTES, stream>>>(
-        wave, (long long)stride_samples, n_samples, n_frames, (unsigned)total_frames, n_tiles, log_eps, h->uimg, out);
-  }
+  const long long total_frames = (long long)batch * n_frames;
+  if (total_frames > 0x7fffff00LL) return fail(B200MEL_ERR_BAD_ARG, "mel: batch * frames must fit 31 bits");
+  const int n_tiles = (int)((total_frames + 31) / 32);
+  urban_mel_packed_kernel<<<n_tiles < h->sm_count ? n_tiles : h->sm_count, U2_THREADS, U2_SMEM_BYTES, stream>>>(
+      wave, (long long)stride_samples, n_samples, n_frames, (unsigned)total_frames, n_tiles, log_eps, h->uimg, out);
   if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail_cuda(e, "urban_mel_kernel launch");
+  if (e != cudaSuccess) return fail_cuda(e, "urban_mel_packed_kernel launch");
   return B200MEL_OK;
 }
 
@@ -469,13 +387,6 @@ int b200mel_urban_prep_f32(b200mel_handle* h, const float* audio, int64_t in_str
   if (e != cudaSuccess) return fail_cuda(e, "urban_peak_norm_kernel launch");
   return B200MEL_OK;
 }
-
-#ifdef W_TRACE
-int b200mel_debug_set_trace(void* dev_ptr) {
-  long long* p = (long long*)dev_ptr;
-  return cudaMemcpyToSymbol(g_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
-}
-#endif
 
 // Host-side staging helper: ragged clips (float32 or float64, one pointer per clip) -> one row-major float32 buffer
 // (pinned, ideally) with `dst_stride` floats per row, converting and copying with `threads` host threads.  Only
@@ -521,6 +432,79 @@ int b200mel_host_pack(const void* const* clips, const int64_t* lengths, int32_t 
     if (b < e) work(b, e);
   });
   return B200MEL_OK;
+}
+
+// The reference's call shape in one native call: ragged HOST clips (float32 or float64, per clip) are converted into the
+// pinned staging buffer by the worker pool, and every worker copies its piece to the device as soon as it is
+// converted (plain per-piece cudaMemcpyAsync on the call's stream), so the cast, the PCIe transfer and -- once the last
+// piece is queued -- the kernels overlap instead of running one after the other.
+int b200mel_whisper_logmel_host(b200mel_handle* h, const void* const* clips, const int64_t* lengths,
+                                const uint8_t* is_f64, int32_t n, float* pinned, int64_t width,
+                                int32_t* pinned_lengths, float* dev_wave, int32_t* dev_lengths, float* out,
+                                void* workspace, size_t workspace_bytes, int32_t threads, void* stream_) {
+  if (!h || h->preset != B200MEL_PRESET_WHISPER) return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel_host: handle is not a Whisper-preset handle");
+  if (n < 0) return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel_host: negative batch");
+  if (n == 0) return B200MEL_OK;
+  if (!clips || !lengths || !is_f64 || !pinned || !pinned_lengths || !dev_wave || !dev_lengths || !out)
+    return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel_host: NULL argument");
+  if (width <= 0 || (width & 3)) return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel_host: width must be a positive multiple of 4");
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    const int64_t L = lengths[i] < 0 ? 0 : (lengths[i] > W_NSAMP ? W_NSAMP : lengths[i]);
+    if (L > width) return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel_host: a clip is longer than the staging row");
+    if (L > 0 && !clips[i]) return fail(B200MEL_ERR_BAD_ARG, "whisper_logmel_host: NULL clip pointer");
+    pinned_lengths[i] = (int32_t)L;
+    total += L;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaError_t first_err = cudaSuccess;
+  std::mutex err_mutex;
+  cudaError_t e = cudaMemcpyAsync(dev_lengths, pinned_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync (lengths)");
+  if (total > 0) {
+    int nt = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+    // pieces of >= 128 K samples (0.5 MB of float32): small enough to start the first copy early and to give every
+    // thread several pieces, large enough that a copy is not all launch overhead
+    const int64_t piece = 1 << 17;
+    const int64_t npieces64 = (total + piece - 1) / piece;
+    const int npieces = (int)(npieces64 > 4096 ? 4096 : npieces64);
+    const int64_t per = (total + npieces - 1) / npieces;
+    if (nt > npieces) nt = npieces;
+    const int device = h->device;
+    std::atomic<int> next_piece{0};
+    auto worker = [&](int) {
+      int cur = -1;
+      cudaGetDevice(&cur);
+      if (cur != device) cudaSetDevice(device);
+      for (;;) {
+        const int p = next_piece.fetch_add(1);
+        if (p >= npieces) break;
+        const int64_t begin = per * p, end = per * (p + 1) < total ? per * (p + 1) : total;
+        int64_t pos = 0;
+        for (int i = 0; i < n && pos < end; ++i) {
+          const int64_t L = pinned_lengths[i];
+          const int64_t lo = begin > pos ? begin - pos : 0, hi = (end - pos) < L ? (end - pos) : L;
+          if (lo < hi) {
+            float* d = pinned + (size_t)i * (size_t)width;
+            if (is_f64[i]) {
+              const double* src = (const double*)clips[i];
+              for (int64_t k = lo; k < hi; ++k) d[k] = (float)src[k];
+            } else {
+              memcpy(d + lo, (const float*)clips[i] + lo, (size_t)(hi - lo) * sizeof(float));
+            }
+            const cudaError_t ce = cudaMemcpyAsync(dev_wave + (size_t)i * (size_t)width + lo, d + lo,
+                                                   (size_t)(hi - lo) * sizeof(float), cudaMemcpyHostToDevice, stream);
+            if (ce != cudaSuccess) { std::lock_guard<std::mutex> lk(err_mutex); if (first_err == cudaSuccess) first_err = ce; }
+          }
+          pos += L;
+        }
+      }
+    };
+    if (nt <= 1) worker(0);
+    else PackPool::get().run(nt, worker);
+    if (first_err != cudaSuccess) return fail_cuda(first_err, "cudaMemcpyAsync (audio piece)");
+  }
+  return b200mel_whisper_logmel_f32(h, dev_wave, width, dev_lengths, n, out, workspace, workspace_bytes, stream_);
 }
 
 int64_t b200mel_get_table(int preset, int table, float* dst, int64_t capacity) {

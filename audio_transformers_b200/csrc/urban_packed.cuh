@@ -1,9 +1,8 @@
-// urban_packed.cuh -- urban preset, persistent packed kernel (default; urban.cuh keeps the first kernel behind
-// B200MEL_URBAN_V1=1 for A/B runs).
+// urban_packed.cuh -- urban preset: the fused mel kernel (persistent CTAs, two frames per lane).
 #pragma once
 // ------------------------------------------------------------------------------------------------
 // Replaces TA:transforms/_transforms.py:621-631 (MelSpectrogram.forward) and the torch.log(mel + 1e-9) of
-// REF:urban_sounds/dataset.py:56, like urban_mel_kernel, with the work laid out differently:
+// REF:urban_sounds/dataset.py:56:
 //
 //  * the frames of the whole batch are one flat list g = clip * n_frames + t; a tile is 32 consecutive
 //    entries (no padding slots except in the very last tile), and a persistent CTA per SM walks tiles

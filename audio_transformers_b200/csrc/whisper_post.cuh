@@ -1,22 +1,7 @@
 // whisper_post.cuh -- the clip-floor pass and the attention-mask kernel of the Whisper preset.
 #pragma once
-// In-place clamp: y = max(y, ymax - 2)  (== (max(log10 e, log10 emax - 8) + 4) / 4).
-__global__ void __launch_bounds__(256)
-whisper_clamp_kernel(float* __restrict__ out, const unsigned int* __restrict__ clip_max_bits, int batch) {
-  constexpr int VEC_PER_CLIP = W_NMEL * W_NFRAME / 4;
-  const int clip = blockIdx.y;
-  const float thr = w_norm_log(__uint_as_float(clip_max_bits[clip])) - 2.0f;
-  float4* p = reinterpret_cast<float4*>(out + (size_t)clip * (W_NMEL * W_NFRAME));
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < VEC_PER_CLIP; i += gridDim.x * blockDim.x) {
-    float4 v = p[i];
-    if (v.x < thr || v.y < thr || v.z < thr || v.w < thr) {
-      v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
-      p[i] = v;
-    }
-  }
-}
-
-// The same pass for the 32-frame kernel: the clip maximum is the maximum over the clip's (tile, warp) slots.
+// In-place clamp: y = max(y, ymax - 2)  (== (max(log10 e, log10 emax - 8) + 4) / 4); the clip maximum is the maximum over
+// the clip's (tile, warp) slots.
 // A few resident CTAs per SM loop over (clip, sixteenth of a clip) work items, so that the whole grid is running from the
 // first instant and `launch_dependents` lets the NEXT call's log-mel kernel start underneath this pass.
 #ifndef CL_CTAS_PER_SM

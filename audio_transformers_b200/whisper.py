@@ -15,7 +15,6 @@ There is no CPU fallback: without a CUDA device (or without the built library) a
 """
 from __future__ import annotations
 
-import ctypes
 import logging
 import os
 from typing import Any, Optional, Sequence, Union
@@ -46,12 +45,18 @@ class FeatureBatch(dict):
         return FeatureBatch({k: (v.to(*args, **kwargs) if isinstance(v, torch.Tensor) else v) for k, v in self.items()})
 
 
+_BATCH_FEATURE = None          # resolved on first use: transformers' BatchFeature, or the stand-in above
+
+
 def _batch_feature(data: dict):
-    try:
-        from transformers.feature_extraction_utils import BatchFeature
-        return BatchFeature(data)
-    except Exception:  # transformers absent or broken: keep the same access pattern
-        return FeatureBatch(data)
+    global _BATCH_FEATURE
+    if _BATCH_FEATURE is None:
+        try:
+            from transformers.feature_extraction_utils import BatchFeature
+            _BATCH_FEATURE = BatchFeature
+        except Exception:  # transformers absent or broken: keep the same access pattern
+            _BATCH_FEATURE = FeatureBatch
+    return _BATCH_FEATURE(data)
 
 
 class B200WhisperFeatureExtractor:
@@ -150,51 +155,55 @@ class B200WhisperFeatureExtractor:
                 raise ValueError(f"Only mono-channel audio is supported for input to {_CLASS_NAME}")
         return clips
 
-    def stage_host_batch(self, clips: Sequence[np.ndarray], dev: torch.device, max_length: int):
-        """Ragged host clips -> one pinned (B, T4) staging buffer + int32 lengths, one H2D each.
-        Only ``min(len, max_length)`` samples per clip cross PCIe; padding is never materialised.  The pack (and the
-        float64 -> float32 cast) is done by ``b200mel_host_pack`` on several host threads into one of two cached pinned
-        buffers; the previous copy out of that buffer is awaited first."""
-        n = len(clips)
-        lens64 = np.fromiter((len(c) for c in clips), dtype=np.int64, count=n)
-        width = max(int(np.minimum(lens64, max_length).max()) if n else 0, 4)
-        width = (width + 3) // 4 * 4
+    def _slot(self, dev: torch.device, n: int, width: int) -> dict:
+        """One of two staging slots used in turn (pinned host rows + lengths, their device twins, an event that marks
+        the last use), grown on demand; the previous use of the slot is awaited before it is handed out again."""
         turn = self._stage_turn
         self._stage_turn ^= 1
         slot = self._stage[turn]
-        if slot is None or slot["host"].numel() < n * width or slot["lens"].numel() < n:
-            slot = {"host": torch.empty((max(n * width, 1),), dtype=torch.float32, pin_memory=True),
-                    "lens": torch.empty((max(n, 64),), dtype=torch.int32, pin_memory=True), "event": None}
+        if slot is None or slot["dev"].device != dev or slot["cap"] < n * width or slot["ncap"] < n:
+            cap, ncap = max(n * width, 4), max(n, 64)
+            slot = {"host": torch.empty((cap,), dtype=torch.float32, pin_memory=True),
+                    "lens": torch.empty((ncap,), dtype=torch.int32, pin_memory=True),
+                    "dev": torch.empty((cap,), dtype=torch.float32, device=dev),
+                    "dev_lens": torch.empty((ncap,), dtype=torch.int32, device=dev),
+                    "event": torch.cuda.Event(), "pending": False, "cap": cap, "ncap": ncap}
             self._stage[turn] = slot
-        elif slot["event"] is not None:
+        elif slot["pending"]:
             slot["event"].synchronize()
-        host = slot["host"][: n * width].view(n, width)
-        lens32 = slot["lens"][:n]
+        return slot
+
+    def _features_from_host(self, clips: Sequence[np.ndarray], dev: torch.device):
+        """Ragged host clips (float32 / float64) -> features, through ONE native call: the worker pool casts the clips
+        into the pinned slot, every worker copies its piece to the device as soon as it is converted, then the kernels
+        are enqueued (b200mel_whisper_logmel_host).  Only ``min(len, 480000)`` samples per clip cross PCIe; padding is
+        never materialised.  Returns (features, device lengths view)."""
+        n = len(clips)
+        lens64 = np.fromiter((c.shape[0] for c in clips), dtype=np.int64, count=n)
+        ptrs = np.fromiter((c.__array_interface__["data"][0] for c in clips), dtype=np.uint64, count=n)
+        is64 = np.fromiter((c.dtype == np.float64 for c in clips), dtype=np.uint8, count=n)
+        width = (max(int(min(lens64.max(), self.n_samples)) if n else 0, 4) + 3) // 4 * 4
+        slot = self._slot(dev, n, width)
+        feats = torch.empty((n, self.feature_size, self.nb_max_frames), dtype=torch.float32, device=dev)
+        if n == 0:
+            return feats, slot["dev_lens"][:0]
         lib = _lib.load()
-        for is_f64, dt in ((1, np.float64), (0, np.float32)):
-            idx = [i for i, c in enumerate(clips) if c.dtype == dt]
-            if not idx:
-                continue
-            # rows of one dtype are packed together; the packer writes row j of the pointer list to dst row j, so it
-            # is handed the sub-batch through per-row destination pointers by calling it once per contiguous run
-            run_start = 0
-            while run_start < len(idx):
-                run_end = run_start
-                while run_end + 1 < len(idx) and idx[run_end + 1] == idx[run_end] + 1:
-                    run_end += 1
-                i0, cnt = idx[run_start], run_end - run_start + 1
-                ptrs = (ctypes.c_void_p * cnt)(*[clips[i0 + j].ctypes.data for j in range(cnt)])
-                st = lib.b200mel_host_pack(ptrs, lens64[i0:i0 + cnt].ctypes.data_as(ctypes.c_void_p), cnt, is_f64, max_length,
-                                           ctypes.c_void_p(host[i0].data_ptr()), width,
-                                           ctypes.c_void_p(lens32[i0:].data_ptr()), self._pack_threads)
-                _lib.check(st, "b200mel_host_pack")
-                run_start = run_end + 1
-        wave = host.to(dev, non_blocking=True)
-        lengths = lens32.to(dev, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
-        slot["event"] = ev
-        return wave, lengths, host
+        h = ops._handle(dev, PRESET_WHISPER)
+        stream = torch.cuda.current_stream(dev)
+        ws = ops._whisper_workspace(lib, h, dev, stream.cuda_stream, n)
+        args = (h, ptrs.ctypes.data, lens64.ctypes.data, is64.ctypes.data, n, slot["host"].data_ptr(), width,
+                slot["lens"].data_ptr(), slot["dev"].data_ptr(), slot["dev_lens"].data_ptr(), feats.data_ptr(),
+                ws.data_ptr(), ws.numel(), self._pack_threads, stream.cuda_stream)
+        if dev.index == torch.cuda.current_device():
+            st = lib.b200mel_whisper_logmel_host(*args)
+        else:
+            with torch.cuda.device(dev):
+                st = lib.b200mel_whisper_logmel_host(*args)
+        if st != 0:
+            _lib.check(st, "b200mel_whisper_logmel_host")
+        slot["event"].record(stream)
+        slot["pending"] = True
+        return feats, slot["dev_lens"][:n]
 
     # -- the call -----------------------------------------------------------------------------------
     def __call__(self, raw_speech, truncation: bool = True, pad_to_multiple_of: Optional[int] = None,
@@ -215,7 +224,7 @@ class B200WhisperFeatureExtractor:
                 "Failing to do so can result in silent errors that might be hard to debug.")
         if do_normalize:
             raise NotImplementedError("do_normalize=True is not supported by the fused kernel (no CPU fallback)")
-        if padding not in ("max_length", True) or not truncation or pad_to_multiple_of is not None:
+        if str(getattr(padding, "value", padding)) != "max_length" or not truncation or pad_to_multiple_of is not None:
             raise NotImplementedError("only padding='max_length', truncation=True, pad_to_multiple_of=None are supported")
         if max_length is not None and max_length != self.n_samples:
             raise NotImplementedError(f"max_length must be {self.n_samples} (30 s); the encoder requires 3000 frames")
@@ -244,14 +253,18 @@ class B200WhisperFeatureExtractor:
             if isinstance(raw_speech, torch.Tensor):
                 raw_speech = raw_speech.numpy()
             clips = self._canonicalise(raw_speech)
-            wave, dev_lengths, _ = self.stage_host_batch(clips, dev, self.n_samples)
-        feats = ops.whisper_logmel(wave, dev_lengths)
+            feats, dev_lengths = self._features_from_host(clips, dev)
+            wave = None
+        if wave is not None:
+            feats = ops.whisper_logmel(wave, dev_lengths)
 
         data = {"input_features": feats}
         want_mask = self.return_attention_mask if return_attention_mask is None else return_attention_mask
         if want_mask:
             if dev_lengths is None:
                 dev_lengths = torch.full((wave.shape[0],), min(wave.shape[1], self.n_samples), dtype=torch.int32, device=dev)
+            elif dev_lengths.dtype != torch.int32:
+                dev_lengths = dev_lengths.to(torch.int32)
             data["attention_mask"] = ops.whisper_frame_mask(dev_lengths)
         if rt != "pt":
             # HF hands back numpy unless return_tensors="pt"; that means a device->host copy here

@@ -30,8 +30,10 @@
  *   - Return value: 0 on success, a negative b200mel_status otherwise.  The message for the
  *     calling thread's last failure is available from b200mel_last_error().  Nothing throws or
  *     exits across this boundary.
- *   - A handle is immutable after creation; concurrent calls from several host threads or
- *     streams are safe as long as each call uses its own workspace.
+ *   - A handle is immutable after creation (the optional b200mel_profile_begin/end pair excepted, which
+ *     is not thread-safe); concurrent calls from several host threads or streams are safe as long as
+ *     each call uses its own workspace.
+ *   - The caller's current CUDA device must be the handle's device when a launching entry point is called.
  *   - There is no CPU path: on a machine without a compute-capability-10.x device
  *     b200mel_create fails with B200MEL_ERR_UNSUPPORTED_ARCH / B200MEL_ERR_CUDA.
  */
@@ -136,6 +138,20 @@ int b200mel_urban_prep_f32(b200mel_handle* h, const float* audio, int64_t in_str
  * first use, re-created in a forked child); concurrent callers are serialised. */
 int b200mel_host_pack(const void* const* clips, const int64_t* lengths, int32_t n, int32_t src_is_f64,
                       int64_t max_samples, float* dst, int64_t dst_stride, int32_t* out_lengths, int32_t threads);
+
+/* The reference's call shape in one call (REF:whisper_finetune/dataset.py:57-62: the extractor is handed HOST numpy arrays,
+ * float64 as `datasets` yields them; HF casts and pads on the host, feature_extraction_whisper.py:281-303).  n ragged HOST
+ * clips (clips[i] is float64 when is_f64[i] != 0, else float32; only min(lengths[i], 480000) samples are used) are cast into
+ * the caller's PINNED staging buffer `pinned` ([n][width] floats, width % 4 == 0, width >= every used length) by the
+ * library's worker threads, each of which copies its piece to `dev_wave` ([n][width], device) with cudaMemcpyAsync on
+ * `stream` as soon as the piece is converted; `pinned_lengths` (pinned, n int32) / `dev_lengths` (device) receive the used
+ * lengths; then b200mel_whisper_logmel_f32 is enqueued on the same stream.  The call returns when everything is enqueued;
+ * `pinned` and `pinned_lengths` must stay untouched until the copies have run (record an event on `stream`).  The handle's
+ * device is made current on the worker threads; the caller's current device must be the handle's device. */
+int b200mel_whisper_logmel_host(b200mel_handle* h, const void* const* clips, const int64_t* lengths,
+                                const uint8_t* is_f64, int32_t n, float* pinned, int64_t width,
+                                int32_t* pinned_lengths, float* dev_wave, int32_t* dev_lengths, float* out,
+                                void* workspace, size_t workspace_bytes, int32_t threads, void* stream);
 
 /* Optional per-kernel timing for benchmarks: between profile_begin and profile_end every call on
  * this handle brackets its dominant kernel (the fused log-mel kernel, not the clip-floor pass)

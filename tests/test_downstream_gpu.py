@@ -3,11 +3,13 @@ the CUDA path must drive the reference's model to the SAME greedy token ids and 
 the features of the reference's own extractor.
 
 Real whisper-tiny weights and the tokenizer are not available offline, so -- as SURVEY.md prescribes -- the model
-is a seeded random-init ``EmotionWhisperModel(WhisperConfig(), num_emotions_classes=10)``.  Its definition is
-restated here from REF:whisper_finetune/model.py:6-18 (composition) and :57-97 (sequence-level branch of
-forward), because the reference tree is not present on the GPU box.  Generation settings are those of
-REF:whisper_finetune/evaluate_simple.py:125-135 (token budget shortened).
+is a seeded random-init ``EmotionWhisperModel(WhisperConfig(), num_emotions_classes=10)``: the reference's own class
+(REF:whisper_finetune/model.py) when the reference tree is present, else its restatement below (composition :6-18,
+sequence-level branch of forward :57-97) -- the tree does not travel to the GPU box.  32 clips, eight of each signal
+class, generation settings and token budget of REF:whisper_finetune/evaluate_simple.py:125-135.
 """
+import importlib.util
+import os
 import numpy as np
 import pytest
 import torch
@@ -17,9 +19,23 @@ from audio_transformers_b200 import signals
 pytestmark = pytest.mark.gpu
 
 
-def _build_model():
-    tr = pytest.importorskip("transformers")
-    from transformers import WhisperConfig, WhisperForConditionalGeneration, WhisperPreTrainedModel
+REF_MODEL = "/root/reference/whisper_finetune/model.py"
+
+
+def _reference_class():
+    """The reference's own EmotionWhisperModel, or None when the tree is not there (the GPU box)."""
+    if not os.path.exists(REF_MODEL):
+        return None
+    import sys
+    spec = importlib.util.spec_from_file_location("ref_whisper_model", REF_MODEL)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod.EmotionWhisperModel
+
+
+def _restated_class():
+    from transformers import WhisperForConditionalGeneration, WhisperPreTrainedModel
 
     class EmotionWhisperModel(WhisperPreTrainedModel):           # REF:whisper_finetune/model.py:6-18
         def __init__(self, config, num_emotions_classes=10):
@@ -35,15 +51,25 @@ def _build_model():
             return {"logits": outputs.logits,
                     "emotion_logits": self.emotion_classifier(torch.mean(hidden_states, dim=1))}
 
+    return EmotionWhisperModel
+
+
+def _build_model():
+    tr = pytest.importorskip("transformers")
+    from transformers import WhisperConfig
+    cls = _reference_class()
+    print("model class:", "the reference's own EmotionWhisperModel" if cls is not None else "restatement (reference tree absent)")
+    if cls is None:
+        cls = _restated_class()
     torch.manual_seed(1234)
-    model = EmotionWhisperModel(WhisperConfig(), num_emotions_classes=10).eval().cuda()
-    return tr, model
+    return tr, cls(WhisperConfig(), num_emotions_classes=10).eval().cuda()
 
 
 def test_greedy_ids_and_emotion_argmax_identical():
     tr, model = _build_model()
     from audio_transformers_b200 import B200WhisperFeatureExtractor
-    clips = [signals.whisper_clip(i, seed=31, n_samples=n) for i, n in enumerate((480000, 480000, 480000, 480000, 200000, 64000))]
+    lens = [480000] * 24 + [200000, 64000, 333333, 16000, 479999, 160000, 96000, 31999]
+    clips = [signals.whisper_clip(i, seed=31, n_samples=n) for i, n in enumerate(lens)]       # classes cycle with i
     ref_fe = tr.WhisperFeatureExtractor()
     ref = ref_fe([c.astype(np.float64) for c in clips], sampling_rate=16000, return_tensors="pt").input_features.cuda()
     ours = B200WhisperFeatureExtractor(device="cuda")(clips, sampling_rate=16000, return_tensors="pt").input_features
@@ -54,12 +80,17 @@ def test_greedy_ids_and_emotion_argmax_identical():
     eos = model.config.eos_token_id
 
     def run(feats):
+        ids_all, emo_all = [], []
         with torch.no_grad():
-            ids = model.whisper.generate(feats, max_new_tokens=24, eos_token_id=eos, pad_token_id=eos, do_sample=False,
-                                         no_repeat_ngram_size=3, repetition_penalty=1.15, length_penalty=-0.5,
-                                         forced_decoder_ids=None)
-            out = model(input_features=feats, decoder_input_ids=ids)
-        return ids, out["emotion_logits"]
+            for b0 in range(0, feats.shape[0], 4):                     # evaluate_simple.py runs batch 4
+                f = feats[b0:b0 + 4]
+                ids = model.whisper.generate(f, max_new_tokens=100, eos_token_id=eos, pad_token_id=eos, do_sample=False,
+                                             no_repeat_ngram_size=3, repetition_penalty=1.15, length_penalty=-0.5,
+                                             forced_decoder_ids=None)
+                out = model(input_features=f, decoder_input_ids=ids)
+                ids_all.append(torch.nn.functional.pad(ids, (0, 128 - ids.shape[1]), value=-1))
+                emo_all.append(out["emotion_logits"])
+        return torch.cat(ids_all), torch.cat(emo_all)
 
     ids_ref, emo_ref = run(ref)
     ids_ours, emo_ours = run(ours)

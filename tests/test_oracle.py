@@ -128,6 +128,15 @@ def test_attention_mask_rescale():
     assert m.sum(axis=1).tolist() == [1, 1, 2, 3000, 3000]
 
 
+def test_attention_mask_vs_live_hf():
+    """HF:models/whisper/feature_extraction_whisper.py:328-337 with return_attention_mask=True, element by element."""
+    tr = pytest.importorskip("transformers")
+    lens = [1, 159, 160, 161, 319, 320, 321, 4000, 479999, 480000, 480001, 600000]
+    clips = [np.full(n, 0.01, dtype=np.float32) for n in lens]
+    ref = tr.WhisperFeatureExtractor()(clips, sampling_rate=16000, return_tensors="np", return_attention_mask=True)
+    assert np.array_equal(O.whisper_attention_mask(lens), ref["attention_mask"])
+
+
 def test_urban_oracle_vs_golden(ugold):
     wave = signals.urban_batch(int(ugold["batch"]), seed=int(ugold["seed"]))
     for dt in (np.float32, np.float64):

@@ -43,14 +43,6 @@ def test_unsupported_options_fail_loudly():
         B200MelSpectrogram(sample_rate=16000)
 
 
-def test_stereo_is_rejected_like_hf():
-    if not torch.cuda.is_available():
-        pytest.skip("canonicalisation runs after the device check")
-    fe = B200WhisperFeatureExtractor()
-    with pytest.raises(ValueError, match="Only mono-channel audio"):
-        fe(np.zeros((2, 2, 100), np.float32), sampling_rate=16000)
-
-
 def test_processor_passthrough():
     class Tok:
         pad_token_id, eos_token_id = 50257, 50256

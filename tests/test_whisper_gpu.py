@@ -14,6 +14,7 @@ from oracle import logmel_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -153,23 +154,42 @@ def test_live_hf_extractor(ops):
     assert err.max() <= TOL
 
 
-@pytest.mark.parametrize("stride", [480000, 480004, 500000, 20600, 20604, 31000, 284, 280])
-def test_tma_and_generic_staging_agree(ops, stride, monkeypatch):
-    """Interior tiles arrive through one TMA box per tile, edge tiles through ordinary stores into the same
-    layout.  Both must give the same bits for every row stride the ABI accepts (the tensor map's extents depend
-    on it; 20600/20604 straddle the first stride that has an interior tile at all, 284/280 the smallest map)."""
+_STRIDES = [480000, 480004, 500000, 20600, 20604, 31000, 284, 280]
+
+
+def _stride_case(ops, stride):
     rng = np.random.default_rng(stride)
     n = min(stride, 480000)
     host = (0.1 * rng.standard_normal((3, stride))).astype(np.float32)
-    lens = torch.tensor([n, max(1, n - 777), max(1, n // 2)], dtype=torch.int32).cuda()
-    wave = torch.from_numpy(host).cuda()
-    a = ops.whisper_logmel(wave, lens).cpu().numpy()
-    monkeypatch.setenv("B200MEL_DEBUG_NO_TMA", "1")
-    b = ops.whisper_logmel(wave, lens).cpu().numpy()
-    monkeypatch.delenv("B200MEL_DEBUG_NO_TMA")
-    assert np.array_equal(a, b)
-    ref = O.whisper_logmel([host[i, :int(lens[i])] for i in range(3)])
-    assert np.abs(a - ref).max() <= TOL
+    lens = [n, max(1, n - 777), max(1, n // 2)]
+    out = ops.whisper_logmel(torch.from_numpy(host).cuda(), torch.tensor(lens, dtype=torch.int32).cuda()).cpu().numpy()
+    return host, lens, out
+
+
+def test_tma_and_generic_staging_agree(ops, tmp_path):
+    """Interior tiles arrive through one TMA box per tile, edge tiles through ordinary stores into the same
+    layout.  Both must give the same bits for every row stride the ABI accepts (the tensor map's extents depend
+    on it; 20600/20604 straddle the first stride that has an interior tile at all, 284/280 the smallest map).
+    The all-stores variant is a property of the handle (B200MEL_DEBUG_NO_TMA=1 when it is created, a test hook), so
+    it runs in a child process."""
+    import subprocess
+    import sys
+    script = tmp_path / "no_tma.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        "from audio_transformers_b200 import ops\n"
+        "import test_whisper_gpu as T\n"
+        "np.savez(sys.argv[1], **{str(s): T._stride_case(ops, s)[2] for s in T._STRIDES})\n")
+    env = dict(os.environ, B200MEL_DEBUG_NO_TMA="1")
+    dump = str(tmp_path / "no_tma.npz")
+    subprocess.run([sys.executable, str(script), dump], check=True, env=env, timeout=600)
+    other = np.load(dump)
+    for stride in _STRIDES:
+        host, lens, a = _stride_case(ops, stride)
+        assert np.array_equal(a, other[str(stride)]), stride
+        ref = O.whisper_logmel([host[i, :lens[i]] for i in range(3)])
+        assert np.abs(a - ref).max() <= TOL, stride
 
 
 def test_cuda_graph_capture_and_replay(ops):
@@ -226,3 +246,123 @@ def test_unaligned_inputs_are_repacked(ops):
 def test_cpu_tensor_fails_loudly(ops):
     with pytest.raises((RuntimeError, NotImplementedError)):
         ops.whisper_logmel(torch.zeros(1, 480000), None)
+
+
+def test_column_sliced_view_without_lengths(ops):
+    """A row-sliced view of a wider buffer (aligned pointer, stride(0) != T) and lengths=None: the clips are the
+    T visible samples of each row, not the whole row stride."""
+    big = torch.from_numpy(signals.whisper_batch(3, seed=23)).cuda()            # (3, 480000)
+    view = big[:, :160000]
+    assert view.stride(0) == 480000 and view.data_ptr() % 16 == 0
+    out = ops.whisper_logmel(view, None).cpu().numpy()
+    ref = O.whisper_logmel([c[:160000] for c in big.cpu().numpy()])
+    assert np.abs(out - ref).max() <= TOL
+    # lengths longer than the view are clamped to it; lengths on another device type are rejected
+    lens = torch.tensor([999999, 160000, 5], dtype=torch.int32).cuda()
+    out2 = ops.whisper_logmel(view, lens).cpu().numpy()
+    assert np.array_equal(out2[:2], out[:2])
+    with pytest.raises((ValueError, RuntimeError)):
+        ops.whisper_logmel(view, torch.tensor([1, 2, 3], dtype=torch.int32))
+
+
+# ---- the reference's call shapes, end to end through the shims, against the live HF extractor ---------------------
+def _hf():
+    tr = pytest.importorskip("transformers")
+    return tr.WhisperFeatureExtractor()
+
+
+def test_input_canonicalisation_vs_live_hf():
+    """HF:models/whisper/feature_extraction_whisper.py:274-292: float64 arrays (what `datasets` yields and the reference
+    passes, REF:whisper_finetune/dataset.py:57-62), lists of them, a 2-D array, a list of Python floats, a mixed
+    float32 / float64 list, a tuple -- all through the native cast + H2D + kernel route."""
+    from audio_transformers_b200 import B200WhisperFeatureExtractor
+    hf, fe = _hf(), B200WhisperFeatureExtractor(device="cuda")
+    c = [signals.whisper_clip(i, seed=41, n_samples=n) for i, n in enumerate((480000, 77777, 160000, 480000))]
+    cases = {
+        "one float64 array": c[1].astype(np.float64),
+        "one float32 array": c[0],
+        "list of float64 arrays": [x.astype(np.float64) for x in c],
+        "mixed float32 / float64 list": [c[0].astype(np.float64), c[1], c[2].astype(np.float64), c[3]],
+        "tuple of arrays": tuple(x.astype(np.float64) for x in c[:2]),
+        "2-D float64 array": np.stack([c[0], c[3]]).astype(np.float64),
+        "2-D float32 array": np.stack([c[0], c[3]]),
+        "list of Python floats": [float(v) for v in c[1][:4000]],
+        "int16-valued integer array": (c[2][:30000] * 1000).astype(np.int32),
+    }
+    for name, raw in cases.items():
+        ref = hf(raw, sampling_rate=16000, return_tensors="pt").input_features.numpy()
+        got = fe(raw, sampling_rate=16000, return_tensors="pt").input_features
+        assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == ref.shape, name
+        err = float(np.abs(got.cpu().numpy() - ref).max())
+        print(f"{name:32s} max-abs vs live HF {err:.2e}")
+        assert err <= TOL, (name, err)
+    # return_tensors=None / "np": numpy on the host, like HF
+    got = fe(c[1].astype(np.float64), sampling_rate=16000)
+    assert isinstance(got["input_features"], np.ndarray) and got["input_features"].shape == (1, 80, 3000)
+    # repeated calls reuse the two staging slots: the third call must not disturb the first result
+    a = fe(c[0].astype(np.float64), sampling_rate=16000, return_tensors="pt").input_features
+    fe(c[1].astype(np.float64), sampling_rate=16000, return_tensors="pt")
+    fe(c[2].astype(np.float64), sampling_rate=16000, return_tensors="pt")
+    ref0 = hf(c[0].astype(np.float64), sampling_rate=16000, return_tensors="pt").input_features.numpy()
+    assert np.abs(a.cpu().numpy() - ref0).max() <= TOL
+
+
+def test_stereo_and_wrong_rate_are_rejected_like_hf():
+    from audio_transformers_b200 import B200WhisperFeatureExtractor
+    hf, fe = _hf(), B200WhisperFeatureExtractor(device="cuda")
+    stereo = np.zeros((2, 2, 100), np.float32)
+    with pytest.raises(ValueError, match="Only mono-channel audio"):
+        hf(stereo, sampling_rate=16000)
+    with pytest.raises(ValueError, match="Only mono-channel audio"):
+        fe(stereo, sampling_rate=16000)
+    for bad in (hf, fe):
+        with pytest.raises(ValueError, match="sampling rate of 16000"):
+            bad(np.zeros(100, np.float32), sampling_rate=8000)
+    with pytest.raises(NotImplementedError):
+        fe(np.zeros(100, np.float32), sampling_rate=16000, padding=True)        # LONGEST in HF: not what this computes
+    with pytest.raises(NotImplementedError):
+        fe(np.zeros(100, np.float32), sampling_rate=16000, padding="longest")
+
+
+def test_attention_mask_vs_live_hf():
+    """HF:models/whisper/feature_extraction_whisper.py:328-337 (mask[:, ::160]) for the edge lengths."""
+    from audio_transformers_b200 import B200WhisperFeatureExtractor
+    hf, fe = _hf(), B200WhisperFeatureExtractor(device="cuda")
+    lens = (1, 159, 160, 161, 480000, 600000)
+    clips = [signals.whisper_clip(i, seed=43, n_samples=n).astype(np.float64) for i, n in enumerate(lens)]
+    ref = hf(clips, sampling_rate=16000, return_tensors="pt", return_attention_mask=True)
+    got = fe(clips, sampling_rate=16000, return_tensors="pt", return_attention_mask=True)
+    assert tuple(got["attention_mask"].shape) == tuple(ref["attention_mask"].shape) == (len(lens), 3000)
+    assert np.array_equal(got["attention_mask"].cpu().numpy(), ref["attention_mask"].numpy())
+    assert np.abs(got["input_features"].cpu().numpy() - ref["input_features"].numpy()).max() <= TOL
+    # one clip per call, as the reference calls it
+    for c in clips[:4]:
+        r = hf(c, sampling_rate=16000, return_tensors="pt", return_attention_mask=True)
+        g = fe(c, sampling_rate=16000, return_tensors="pt", return_attention_mask=True)
+        assert np.array_equal(g["attention_mask"].cpu().numpy(), r["attention_mask"].numpy())
+
+
+def test_processor_audio_path_vs_live_hf():
+    """HF:models/whisper/processing_whisper.py:31-54 with audio: positional, audio=, audio + text (labels), and the
+    reference's exact line REF:whisper_finetune/dataset.py:58-62."""
+    from audio_transformers_b200 import B200WhisperProcessor
+
+    class Tok:                                        # the tokenizer is passthrough; a stub keeps the test offline
+        pad_token_id, eos_token_id = 50257, 50256
+
+        def __call__(self, text=None, **kw):
+            return {"input_ids": [[7, 8, 9]]}
+
+    hf = _hf()
+    proc = B200WhisperProcessor(tokenizer=Tok(), device="cuda")
+    audio = signals.whisper_clip(5, seed=47, n_samples=200000).astype(np.float64)
+    ref = hf(audio, sampling_rate=16000, return_tensors="pt").input_features
+    a = proc(audio, sampling_rate=16000, return_tensors="pt").input_features.squeeze(0)      # dataset.py:58-62
+    assert a.is_cuda and tuple(a.shape) == (80, 3000)
+    assert float((a.cpu() - ref[0]).abs().max()) <= TOL
+    b = proc(audio=audio, sampling_rate=16000, return_tensors="pt")
+    assert torch.equal(b["input_features"].squeeze(0), a) and torch.equal(b.input_features.squeeze(0), a)
+    both = proc(audio=audio, text="hello", sampling_rate=16000, return_tensors="pt")
+    assert both["labels"] == [[7, 8, 9]] and torch.equal(both["input_features"].squeeze(0), a)
+    assert torch.equal(proc.feature_extractor(audio, sampling_rate=16000, return_tensors="pt").input_features.squeeze(0), a)
+    assert a.to("cuda") is a                          # REF:whisper_finetune/inference.py:154 `.to(device)` is a no-op
