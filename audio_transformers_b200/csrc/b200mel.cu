@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <functional>
@@ -61,6 +62,33 @@ int fail_cuda(cudaError_t e, const char* where) {
 
 }  // namespace
 
+// float64 -> float32 into the pinned staging buffer with non-temporal stores: the destination is only read by the copy
+// engine, so pulling its lines into the cache first (write-allocate) would be a third of the cast's memory traffic.
+#if defined(__x86_64__)
+#include <immintrin.h>
+namespace {
+__attribute__((target("avx2"))) void cast_f64_f32_avx2(const double* __restrict__ s, float* __restrict__ d, int64_t n) {
+  int64_t k = 0;
+  for (; k < n && ((uintptr_t)(d + k) & 31); ++k) d[k] = (float)s[k];
+  for (; k + 8 <= n; k += 8) {
+    const __m128 lo = _mm256_cvtpd_ps(_mm256_loadu_pd(s + k)), hi = _mm256_cvtpd_ps(_mm256_loadu_pd(s + k + 4));
+    _mm256_stream_ps(d + k, _mm256_set_m128(hi, lo));
+  }
+  for (; k < n; ++k) d[k] = (float)s[k];
+  _mm_sfence();
+}
+}  // namespace
+#endif
+namespace {
+void cast_f64_f32(const double* __restrict__ s, float* __restrict__ d, int64_t n) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) { cast_f64_f32_avx2(s, d, n); return; }
+#endif
+  for (int64_t k = 0; k < n; ++k) d[k] = (float)s[k];
+}
+}  // namespace
+
 // Persistent host worker pool for b200mel_host_pack: creating threads per call costs more than converting a 30 s
 // clip (measured: 0.33 ms on one thread, 0.68 ms when 7 fresh threads share the clip).  Workers sleep on a condition
 // variable between calls.  One job at a time (callers are serialised by a mutex); a process that forked after the
@@ -83,6 +111,7 @@ class PackPool {
     grow(parts - 1);
     std::unique_lock<std::mutex> lk(m_);
     fn_ = &fn; parts_ = parts; next_ = 0; pending_ = parts; ++generation_;
+    gen_hint_.store(generation_, std::memory_order_release);
     const unsigned long long mine = generation_;
     cv_.notify_all();
     drain(lk, mine);                                   // the caller works too, it does not just wait
@@ -112,6 +141,19 @@ class PackPool {
     unsigned long long seen = 0;
     std::unique_lock<std::mutex> lk(m_);
     for (;;) {
+      if (generation_ == seen) {
+        // calls tend to come back to back (one per clip in the reference's loop): look for the next job for ~100 us
+        // before going to sleep -- waking a sleeping thread costs several times the work it is then given
+        lk.unlock();
+        const auto t0 = std::chrono::steady_clock::now();
+        while (gen_hint_.load(std::memory_order_acquire) == seen &&
+               std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(100)) {
+#if defined(__x86_64__)
+          __builtin_ia32_pause();
+#endif
+        }
+        lk.lock();
+      }
       cv_.wait(lk, [&] { return generation_ != seen; });
       seen = generation_;
       drain(lk, seen);
@@ -123,6 +165,7 @@ class PackPool {
   const std::function<void(int)>* fn_ = nullptr;
   int next_ = 0, parts_ = 0, pending_ = 0;
   unsigned long long generation_ = 0;
+  std::atomic<unsigned long long> gen_hint_{0};      // copy of generation_ the workers may poll without the lock
 };
 }  // namespace
 
@@ -416,8 +459,7 @@ int b200mel_host_pack(const void* const* clips, const int64_t* lengths, int32_t 
       if (lo < hi) {
         float* d = dst + (size_t)i * (size_t)dst_stride;
         if (src_is_f64) {
-          const double* s = (const double*)clips[i];
-          for (int64_t k = lo; k < hi; ++k) d[k] = (float)s[k];
+          cast_f64_f32((const double*)clips[i] + lo, d + lo, hi - lo);
         } else {
           memcpy(d + lo, (const float*)clips[i] + lo, (size_t)(hi - lo) * sizeof(float));
         }
@@ -465,7 +507,7 @@ int b200mel_whisper_logmel_host(b200mel_handle* h, const void* const* clips, con
     int nt = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
     // pieces of >= 128 K samples (0.5 MB of float32): small enough to start the first copy early and to give every
     // thread several pieces, large enough that a copy is not all launch overhead
-    const int64_t piece = 1 << 17;
+    const int64_t piece = total <= (1 << 19) ? (1 << 16) : (1 << 17);
     const int64_t npieces64 = (total + piece - 1) / piece;
     const int npieces = (int)(npieces64 > 4096 ? 4096 : npieces64);
     const int64_t per = (total + npieces - 1) / npieces;
@@ -487,8 +529,7 @@ int b200mel_whisper_logmel_host(b200mel_handle* h, const void* const* clips, con
           if (lo < hi) {
             float* d = pinned + (size_t)i * (size_t)width;
             if (is_f64[i]) {
-              const double* src = (const double*)clips[i];
-              for (int64_t k = lo; k < hi; ++k) d[k] = (float)src[k];
+              cast_f64_f32((const double*)clips[i] + lo, d + lo, hi - lo);
             } else {
               memcpy(d + lo, (const float*)clips[i] + lo, (size_t)(hi - lo) * sizeof(float));
             }

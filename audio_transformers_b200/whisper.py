@@ -59,6 +59,21 @@ def _batch_feature(data: dict):
     return _BATCH_FEATURE(data)
 
 
+def default_pack_threads() -> int:
+    """Host threads one process may use for the cast into pinned memory: the cores it may run on, shared fairly with
+    the other ranks of the node (torchrun exports LOCAL_WORLD_SIZE), 16 at most -- the cast is bound by memory
+    bandwidth long before that, and eight ranks with 16 threads each would only fight over the same cores."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        cores = os.cpu_count() or 1
+    try:
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        ranks = 1
+    return max(1, min(16, cores // ranks))
+
+
 class B200WhisperFeatureExtractor:
     """GPU log-mel extractor with ``WhisperFeatureExtractor``'s interface.
 
@@ -94,7 +109,7 @@ class B200WhisperFeatureExtractor:
         # two pinned staging buffers used in turn, so that packing batch k+1 overlaps the H2D copy of batch k
         self._stage = [None, None]
         self._stage_turn = 0
-        self._pack_threads = max(1, min(16, os.cpu_count() or 1))
+        self._pack_threads = default_pack_threads()
 
     # -- attributes the reference's notebook prints (experiments.ipynb:558-573) --------------------
     @property

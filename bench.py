@@ -395,29 +395,30 @@ def run_ours(args) -> dict | None:
     clips64 = [[c.astype(np.float64) for c in clips32[p]] for p in range(2)]
     host_out = [torch.empty((B, 80, 3000), dtype=torch.float32).pin_memory() for _ in range(2)]
 
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
     def e2e_step(k):
-        feats = fe(clips64[k % 2], sampling_rate=16000, return_tensors="pt").input_features
-        host_out[k % 2].copy_(feats, non_blocking=True)
+        # steps alternate between two streams, so that the D2H of step k (one copy engine) runs while step k + 1 is
+        # cast on the host and copied in (the other copy engine); every step does its own H2D and its own D2H
+        s = streams[k % 2]
+        with torch.cuda.stream(s):
+            feats = fe(clips64[k % 2], sampling_rate=16000, return_tensors="pt").input_features
+            host_out[k % 2].copy_(feats, non_blocking=True)
 
     Ke = max(2, min(K, 100))
-    for k in range(min(W, 4)):
+    for k in range(min(max(W, 2), 4)):
         e2e_step(k)
     barrier()
     te0 = time.perf_counter()
-    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ee0.record()
     for k in range(Ke):
         e2e_step(k)
-    ee1.record()
     barrier()
     e2e_wall = time.perf_counter() - te0
     # the region's time is the host wall clock between the two synchronising barriers (the cast runs on the host: a
-    # pair of device events would not see it); the events are the cross-check
+    # pair of device events would not see it)
     e2e_ms_total = e2e_wall * 1e3
-    e2e_dev_ms = ee0.elapsed_time(ee1)
 
     # secondary: a pre-collated pinned float32 batch (one H2D, no cast), two streams
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
     def pinned_step(k):
         s = streams[k % 2]
@@ -485,7 +486,7 @@ def run_ours(args) -> dict | None:
                    "l2": f"inputs rotate over {N_POOL} distinct {B * 1.92:.0f} MB batches (> 126 MB L2)",
                    "timing": "CUDA events on the launch stream, max over ranks", "launch": launch_mode,
                    "ms_per_step_median": statistics.median(blk_ms), "ms_per_step_best": min(blk_ms), "timing_blocks": nblk,
-                   "e2e_steps": Ke, "e2e_wall_s": round(e2e_wall, 4), "e2e_device_events_s": round(e2e_dev_ms * 1e-3, 4), "checksum": checksum,
+                   "e2e_steps": Ke, "e2e_wall_s": round(e2e_wall, 4), "checksum": checksum,
                    "gpu_launches_scope": "per rank and step: fused log-mel kernel (TMA-fed) + clip-floor pass; no memset"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
@@ -498,7 +499,7 @@ def run_ours(args) -> dict | None:
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 480000 * 4,
                 "d2h_bytes_per_step": B * 80 * 3000 * 4,
                 "api": "B200WhisperFeatureExtractor(list of 64 float64 numpy clips, sampling_rate=16000, return_tensors='pt')"
-                       ".input_features -> pinned host tensor",
+                       ".input_features -> pinned host tensor; steps alternate between two CUDA streams; host wall clock",
                 "host_cast_bytes_per_step": B * 480000 * 8, "other_call_shapes": sub},
         "gpu_launches": 2 * K,
         "clocks": clocks,
