@@ -1,16 +1,16 @@
-// whisper_tile32.cuh -- the default Whisper kernel: 32-frame tiles, two CTAs per SM.
+// whisper_tile32.cuh -- the Whisper log-mel kernel: 32-frame tiles, one 512-thread CTA per SM running two halves.
 #pragma once
 // ================================================================================================
-// Whisper kernel, 32-frame tiles, TWO CTAs per SM
+// Replaces HF:models/whisper/feature_extraction_whisper.py:135-164 (_torch_extract_fbank_features) plus the pad / trim
+// of HF:feature_extraction_sequence_utils.py:263-278,327-332, up to the clip-wide floor (whisper_post.cuh).
 //
-// Same arithmetic and the same three stages as whisper_logmel_kernel, re-cut so that a tile needs 107 KB of
-// shared memory instead of 208 KB: two independent 256-thread CTAs share an SM, and while one waits at a block
-// barrier or on its shared-memory loads the other one computes.  (The 64-frame kernel is latency bound: 16 warps,
-// all in the same phase.)  What makes the half-size tile possible without giving up the packed f32x2 arithmetic:
-//   pass 1   a warp is 8 frame pairs x 4 classes anyway (w_pass1), so a 32-frame tile is simply 2 x 4 warp tasks;
+// ONE 512-thread CTA per SM runs TWO independent halves (8 warps each, own audio / E / P buffers of 103 KB, own named
+// barrier and mbarrier): while one half waits at its barrier or on shared-memory loads the other computes.  A half
+// works on 32-frame tiles; every FP32 value is a packed float2 holding the same quantity of two frames:
+//   pass 1   a warp is 8 frame pairs x 4 residue classes: windowed real 25-point DFTs (Good-Thomas 16 x 25);
 //   pass 2   the 16-point DFT is the same code for every k2 (no twiddles), so a warp takes 16 columns x 2 tasks;
 //   mel      a warp takes the 16 columns unpacked: lanes 0..15 the first frame of each pair, lanes 16..31 the
-//            second, scalar FFMA with the same immediates (the FMA pipe time per frame is unchanged).
+//            second, scalar FFMA with immediate weights (the FMA pipe time per frame is unchanged).
 // ================================================================================================
 constexpr int V_TILE = 32, V_WARPS = 8;                                          // per half: 8 warps, one 32-frame tile in flight
 constexpr int V_HALVES = 2, V_HALF_THREADS = V_WARPS * 32, V_THREADS = V_HALVES * V_HALF_THREADS;
@@ -94,7 +94,7 @@ __device__ __forceinline__ void v_stage_generic(const WTile& t, float* __restric
   }
 }
 
-// pass 1: identical to w_pass1 but for the E layout of this kernel (16 columns per row)
+// pass 1: windowed real 25-point DFT of residue class a for one frame pair per lane (E layout: 16 columns per row)
 __device__ __forceinline__ void v_pass1(int a, const float* __restrict__ audio_lane, float2* __restrict__ e_dst,
                                         const int* __restrict__ s_off, const float* __restrict__ s_win) {
   float2 x[25], o[25];
