@@ -83,6 +83,34 @@ def test_zeros_and_floor(ops):
     assert np.abs(out + 1.5).max() < 1e-6                                      # (-10 + 4) / 4
 
 
+def test_floor_reaches_exactly_the_blocks_below_it(ops):
+    """The clip-floor pass skips every (tile, mel range) block whose smallest energy is already above the floor: clips
+    whose dynamic range crosses the 80 dB line only in places -- a loud burst over very quiet noise, digital silence in
+    the middle, a pure tone (far bins below the floor everywhere), quiet noise alone (nothing to floor) -- must still
+    equal the oracle everywhere, and the floored set must be the oracle's."""
+    rng = np.random.default_rng(77)
+    n = 480000
+    burst = (1e-6 * rng.standard_normal(n)).astype(np.float32)
+    burst[16000:32000] += (0.5 * rng.standard_normal(16000)).astype(np.float32)
+    gap = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    gap[200000:260000] = 0.0
+    t = np.arange(n, dtype=np.float64) / 16000.0
+    tone = (0.8 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+    quiet = (1e-3 * rng.standard_normal(n)).astype(np.float32)
+    ramp = (rng.standard_normal(n) * np.logspace(-7, 0, n)).astype(np.float32)
+    clips = [burst, gap, tone, quiet, ramp, ramp[::-1].copy(), burst[:123457]]
+    out = _run(ops, clips)
+    ref = O.whisper_logmel(clips, dtype=np.float32)
+    assert np.abs(out - ref).max() <= TOL
+    for i in range(len(clips)):
+        floor = ref[i].min()
+        assert abs(float(out[i].min()) - float(floor)) <= TOL
+        # nothing stays under the clip's floor, and what the oracle floored is floored here
+        assert (out[i] >= out[i].max() - 2.0 - 1e-6).all()
+        assert np.abs(out[i][ref[i] <= floor + 1e-7] - floor).max() <= TOL
+    assert (ref[3] > ref[3].min() + 1e-3).mean() > 0.99                         # the "nothing to floor" clip is one
+
+
 def test_lengths_none_means_full_stride(ops):
     clips = signals.whisper_batch(3, seed=5)
     wave = torch.from_numpy(clips).cuda()
