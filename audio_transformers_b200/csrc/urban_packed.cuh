@@ -202,8 +202,8 @@ __device__ __forceinline__ void u2_mel(const U2Geom& G, int tile, int group, int
     const int4 f = gent[e];
     const float2* __restrict__ pp = p2 + f.x * 16;
     const float4* __restrict__ ww = reinterpret_cast<const float4*>(mw + f.z);
-    // 8 taps per trip (the zero padding may read a few rows past the filter, and past P into the tables: finite
-    // values times zero), two accumulation chains
+    // 8 taps per trip over a run that u2_build_image keeps inside P (zero weights pad it to 8 k rows of the same
+    // frame pair), two accumulation chains
     float2 a0 = make_float2(0.0f, 0.0f), a1 = a0;
 #pragma unroll 1
     for (int j = 0; j < f.y; j += 8) {
@@ -302,8 +302,14 @@ static void u2_build_image(std::vector<float>& img) {
     goff[gi] = n;
     for (int m = 0; m < 64; ++m)
       if (owner[m] == gorder[gi]) {
-        for (int j = 0; j < host_tab::kUMelLen[m]; ++j) img[U2_IMG_MW + woff + j] = host_tab::c_umelw[host_tab::kUMelOff[m] + j];
-        gent[4 * n + 0] = host_tab::kUMelStart[m]; gent[4 * n + 1] = pad[m];
+        // the padded run of 8 k taps must stay inside P's 513 rows: a filter that ends near the last bin starts its run
+        // earlier and leads with zero weights instead of trailing with them
+        int first = host_tab::kUMelStart[m];
+        const int lead = first + pad[m] > U_NBIN ? first + pad[m] - U_NBIN : 0;
+        first -= lead;
+        if (first < 0) { img.clear(); return; }
+        for (int j = 0; j < host_tab::kUMelLen[m]; ++j) img[U2_IMG_MW + woff + lead + j] = host_tab::c_umelw[host_tab::kUMelOff[m] + j];
+        gent[4 * n + 0] = first; gent[4 * n + 1] = pad[m];
         gent[4 * n + 2] = woff;                    gent[4 * n + 3] = m;
         woff += pad[m];
         ++n;
