@@ -6,7 +6,8 @@ and every entry point fails loudly when it (or a CUDA device) is missing.  See D
 """
 __version__ = "0.1.0"
 
-__all__ = ["B200WhisperFeatureExtractor", "B200WhisperProcessor", "B200MelSpectrogram", "B200UrbanFrontEnd", "ops", "signals"]
+__all__ = ["B200WhisperFeatureExtractor", "B200WhisperProcessor", "B200MelSpectrogram", "B200UrbanFrontEnd", "B200WhisperEncoderStem",
+           "ops", "signals"]
 
 
 def __getattr__(name):
@@ -16,7 +17,10 @@ def __getattr__(name):
     if name in ("B200MelSpectrogram", "B200UrbanFrontEnd"):
         from . import urban
         return getattr(urban, name)
-    if name in ("ops", "signals", "whisper", "urban", "collate"):
+    if name == "B200WhisperEncoderStem":
+        from . import encoder_stem
+        return encoder_stem.B200WhisperEncoderStem
+    if name in ("ops", "signals", "whisper", "urban", "collate", "encoder_stem"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -40,6 +40,9 @@ SYMBOLS = {
     "b200mel_whisper_logmel_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_void_p,
                                                _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                _c.c_size_t, _c.c_int32, _c.c_void_p]),
+    "b200mel_encoder_stem_workspace_bytes": (_c.c_size_t, [_c.c_void_p, _c.c_int32]),
+    "b200mel_encoder_stem_bf16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                             _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "b200mel_profile_begin": (_c.c_int, [_c.c_void_p, _c.c_int32]),
     "b200mel_profile_end": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_double), _c.POINTER(_c.c_int32)]),
     "b200mel_get_table": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_void_p, _c.c_int64]),

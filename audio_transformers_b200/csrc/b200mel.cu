@@ -10,6 +10,7 @@
 // urban.cuh (the pre-step kernels: mono mix, resample, peak normalisation).  DESIGN.md has the layouts and the measurements.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -45,6 +46,7 @@ namespace {
 #include "whisper_post.cuh"
 #include "urban.cuh"
 #include "urban_packed.cuh"
+#include "encoder_stem.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Host side
@@ -216,6 +218,10 @@ int b200mel_create(int device, int preset, b200mel_handle** out) {
     e = cudaFuncSetAttribute(whisper_logmel_kernel32, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(urban_mel_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(es_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ES_SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(es_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ES_SMEM_BYTES);
   if (e != cudaSuccess) { cudaSetDevice(prev); return fail_cuda(e, "cudaFuncSetAttribute"); }
   b200mel_handle* h = new b200mel_handle(device, preset, prop.multiProcessorCount);
   if (preset == B200MEL_PRESET_URBAN) {
@@ -353,6 +359,83 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   whisper_clamp_kernel32<<<grid, CL_THREADS, 0, stream>>>(out, (const float*)workspace, batch, lengths, (long long)stride_samples);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "whisper_clamp_kernel32 launch");
+  return B200MEL_OK;
+}
+
+// ---- encoder stem ----------------------------------------------------------------------------
+static size_t es_a1_bytes(int32_t batch) { return (((size_t)batch * ES_T * ES_K1 * 2) + 1023) & ~(size_t)1023; }
+static size_t es_h_bytes(int32_t batch) { return (((size_t)batch * ES_HROWS * ES_D * 2) + 1023) & ~(size_t)1023; }
+
+size_t b200mel_encoder_stem_workspace_bytes(const b200mel_handle* h, int32_t batch) {
+  if (!h || batch <= 0 || h->preset != B200MEL_PRESET_WHISPER) return 0;
+  return es_a1_bytes(batch) + es_h_bytes(batch);
+}
+
+static bool es_encode(b200mel_handle* h, CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box) {
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  memset(tm, 0, sizeof(*tm));
+  return h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int b200mel_encoder_stem_bf16(b200mel_handle* h, const float* features, int32_t batch, const void* w1, const float* bias1,
+                              const void* w2, const float* bias2, const float* positions, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!h || h->preset != B200MEL_PRESET_WHISPER) return fail(B200MEL_ERR_BAD_ARG, "encoder_stem: handle is not a Whisper-preset handle");
+  if (batch < 0) return fail(B200MEL_ERR_BAD_ARG, "encoder_stem: negative batch");
+  if (batch == 0) return B200MEL_OK;
+  if (!features || !w1 || !bias1 || !w2 || !bias2 || !positions || !out) return fail(B200MEL_ERR_BAD_ARG, "encoder_stem: NULL argument");
+  if (((uintptr_t)features | (uintptr_t)w1 | (uintptr_t)bias1 | (uintptr_t)w2 | (uintptr_t)bias2 | (uintptr_t)positions |
+       (uintptr_t)out | (uintptr_t)workspace) & 15)
+    return fail(B200MEL_ERR_BAD_ALIGN, "encoder_stem: every pointer must be 16-byte aligned");
+  if (!workspace || workspace_bytes < b200mel_encoder_stem_workspace_bytes(h, batch))
+    return fail(B200MEL_ERR_WORKSPACE, "encoder_stem: workspace too small (see b200mel_encoder_stem_workspace_bytes)");
+  if ((long long)batch * 48 > 0x7fffffffLL / 2) return fail(B200MEL_ERR_BAD_ARG, "encoder_stem: batch too large for one launch");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  __nv_bfloat16* a1 = reinterpret_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + es_a1_bytes(batch));
+
+  CUtensorMap tm_a1, tm_w1, tm_h, tm_w2;
+  {
+    // im2col rows of conv1 as (k, -, t, clip); the second dimension exists only so that both GEMMs use 4-D coordinates
+    const cuuint64_t dims[4] = {ES_K1, 1, ES_T, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {ES_K1 * 2, ES_K1 * 2, (cuuint64_t)ES_T * ES_K1 * 2};
+    const cuuint32_t box[4] = {ES_BK, 1, ES_BM, 1};
+    if (!es_encode(h, &tm_a1, a1, 4, dims, strides, box)) return fail(B200MEL_ERR_CUDA, "encoder_stem: tensor map (A1)");
+  }
+  {
+    // rows of h as (channel, row parity, row pair, clip): tap k of output row t' is row 2 t' + k = (pair t' + k / 2, parity k % 2)
+    const cuuint64_t dims[4] = {ES_D, 2, ES_HROWS / 2, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {ES_D * 2, 2 * ES_D * 2, (cuuint64_t)ES_HROWS * ES_D * 2};
+    const cuuint32_t box[4] = {ES_BK, 1, ES_BM, 1};
+    if (!es_encode(h, &tm_h, hid, 4, dims, strides, box)) return fail(B200MEL_ERR_CUDA, "encoder_stem: tensor map (h)");
+  }
+  {
+    const cuuint64_t dims[2] = {ES_K1, ES_D};
+    const cuuint64_t strides[1] = {ES_K1 * 2};
+    const cuuint32_t box[2] = {ES_BK, ES_BN};
+    if (!es_encode(h, &tm_w1, w1, 2, dims, strides, box)) return fail(B200MEL_ERR_CUDA, "encoder_stem: tensor map (W1)");
+  }
+  {
+    const cuuint64_t dims[2] = {ES_K2, ES_D};
+    const cuuint64_t strides[1] = {ES_K2 * 2};
+    const cuuint32_t box[2] = {ES_BK, ES_BN};
+    if (!es_encode(h, &tm_w2, w2, 2, dims, strides, box)) return fail(B200MEL_ERR_CUDA, "encoder_stem: tensor map (W2)");
+  }
+  es_im2col_kernel<<<dim3((ES_T + ES_IC_FRAMES - 1) / ES_IC_FRAMES, batch), ES_IC_THREADS, 0, stream>>>(features, a1, hid);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "es_im2col_kernel launch");
+  EsGemm g1{batch, (ES_T + ES_BM - 1) / ES_BM, ES_T, ES_K1 / ES_BK, ES_K1 / ES_BK, bias1, nullptr, hid};
+  EsGemm g2{batch, (ES_T2 + ES_BM - 1) / ES_BM, ES_T2, ES_K2 / ES_BK, ES_D / ES_BK, bias2, positions, out};
+  const int t1 = batch * g1.mtiles * (ES_D / ES_BN), t2 = batch * g2.mtiles * (ES_D / ES_BN);
+  es_gemm_kernel<0><<<t1 < h->sm_count ? t1 : h->sm_count, ES_THREADS, ES_SMEM_BYTES, stream>>>(tm_a1, tm_w1, g1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "es_gemm_kernel<conv1> launch");
+  es_gemm_kernel<1><<<t2 < h->sm_count ? t2 : h->sm_count, ES_THREADS, ES_SMEM_BYTES, stream>>>(tm_h, tm_w2, g2);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "es_gemm_kernel<conv2> launch");
   return B200MEL_OK;
 }
 

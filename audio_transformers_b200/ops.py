@@ -5,6 +5,7 @@ through its features: the extractor returns numpy, HF:models/whisper/feature_ext
     torch.ops.b200mel.whisper_frame_mask(lengths)   -> (B, 3000) int32
     torch.ops.b200mel.mel_power(wave, log_eps)       -> (B, 64, 1 + T // 512) float32
     torch.ops.b200mel.urban_prep(audio, lengths, orig, new, taps, width, out_samples) -> (B, out_samples) float32
+    torch.ops.b200mel.encoder_stem(features, w1, bias1, w2, bias2, positions) -> (B, 1500, 384) float32
 
 All inputs and outputs live on the same CUDA device; the kernels are enqueued on the current
 stream of that device without any host synchronisation.
@@ -58,13 +59,16 @@ _LIBDEF.define("urban_prep(Tensor audio, Tensor? lengths, int orig_freq, int new
                "int out_samples) -> Tensor")
 
 
+_LIBDEF.define("encoder_stem(Tensor features, Tensor w1, Tensor bias1, Tensor w2, Tensor bias2, Tensor positions) -> Tensor")
+
+
 _workspaces: dict = {}        # (device index, stream, batch) -> zero-initialised workspace tensor
 
 
 def _whisper_workspace(lib, h, dev: torch.device, stream: int, batch: int) -> torch.Tensor:
-    """The kernel's per-clip control words.  They must be zero before the first launch and every launch leaves them
-    zero again (include/b200mel.h), so one buffer per (device, stream, batch) is zeroed once and reused; calls on
-    different streams never share one."""
+    """The per-(clip, tile, warp) maxima the floor pass reduces (include/b200mel.h: no initialisation needed).  One
+    buffer per (device, stream, batch) is kept and reused, so a call allocates nothing; calls on different streams
+    never share one."""
     key = (dev.index, stream, batch)
     ws = _workspaces.get(key)
     if ws is None:
@@ -213,6 +217,46 @@ _LIBDEF.impl("whisper_frame_mask", _whisper_frame_mask_cuda, "CUDA")
 _LIBDEF.impl("mel_power", _mel_power_cuda, "CUDA")
 
 
+def _encoder_stem_cuda(features: torch.Tensor, w1: torch.Tensor, bias1: torch.Tensor, w2: torch.Tensor,
+                       bias2: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+    """HF:models/whisper/modeling_whisper.py:619-625 (whisper-tiny geometry) on the tensor cores; weights in the
+    layout include/b200mel.h describes (encoder_stem.pack_weights builds them)."""
+    for t, name in ((features, "features"), (w1, "w1"), (bias1, "bias1"), (w2, "w2"), (bias2, "bias2"), (positions, "positions")):
+        _require_cuda(t, name)
+        if t.device != features.device:
+            raise RuntimeError(f"b200mel: encoder_stem: `{name}` is on {t.device}, features on {features.device}")
+    if features.dtype != torch.float32 or features.dim() != 3 or tuple(features.shape[1:]) != (W_NMEL, W_NFRAME):
+        raise RuntimeError(f"b200mel: encoder_stem: features must be float32 (B, 80, 3000), got {features.dtype} {tuple(features.shape)}")
+    if w1.dtype != torch.bfloat16 or tuple(w1.shape) != (384, 256) or w2.dtype != torch.bfloat16 or tuple(w2.shape) != (384, 1152):
+        raise RuntimeError("b200mel: encoder_stem: w1 must be bfloat16 (384, 256) and w2 bfloat16 (384, 1152)")
+    for t, shape, name in ((bias1, (384,), "bias1"), (bias2, (384,), "bias2"), (positions, (1500, 384), "positions")):
+        if t.dtype != torch.float32 or tuple(t.shape) != shape:
+            raise RuntimeError(f"b200mel: encoder_stem: `{name}` must be float32 {shape}")
+    features, w1, bias1, w2, bias2, positions = (t.contiguous() for t in (features, w1, bias1, w2, bias2, positions))
+    lib = _lib.load()
+    dev = features.device
+    h = _handle(dev, _lib.PRESET_WHISPER)
+    batch = features.shape[0]
+    out = torch.empty((batch, 1500, 384), dtype=torch.float32, device=dev)
+    if batch == 0:
+        return out
+    nbytes = int(lib.b200mel_encoder_stem_workspace_bytes(h, batch))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.b200mel_encoder_stem_bf16(h, features.data_ptr(), batch, w1.data_ptr(), bias1.data_ptr(), w2.data_ptr(),
+                                                 bias2.data_ptr(), positions.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes,
+                                                 _stream_ptr(dev)), "b200mel_encoder_stem_bf16")
+    return out
+
+
+_LIBDEF.impl("encoder_stem", _encoder_stem_cuda, "CUDA")
+
+
+@torch.library.register_fake("b200mel::encoder_stem")
+def _encoder_stem_fake(features, w1, bias1, w2, bias2, positions):
+    return features.new_empty((features.shape[0], 1500, 384))
+
+
 @torch.library.register_fake("b200mel::whisper_logmel")
 def _whisper_logmel_fake(wave, lengths):
     return wave.new_empty((wave.shape[0], W_NMEL, W_NFRAME), dtype=torch.float32)
@@ -240,6 +284,11 @@ def urban_prep(audio: torch.Tensor, lengths: Optional[torch.Tensor], orig_freq: 
 
 def whisper_logmel(wave: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     return torch.ops.b200mel.whisper_logmel(wave, lengths)
+
+
+def encoder_stem(features: torch.Tensor, w1: torch.Tensor, bias1: torch.Tensor, w2: torch.Tensor, bias2: torch.Tensor,
+                 positions: torch.Tensor) -> torch.Tensor:
+    return torch.ops.b200mel.encoder_stem(features, w1, bias1, w2, bias2, positions)
 
 
 def whisper_frame_mask(lengths: torch.Tensor) -> torch.Tensor:

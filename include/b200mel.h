@@ -97,6 +97,24 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
                                const int32_t* lengths, int32_t batch, float* out,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Whisper preset, the encoder stem that consumes the feature map: replaces
+ * HF:models/whisper/modeling_whisper.py:619-625 for whisper-tiny,
+ *     hidden = gelu(conv2(gelu(conv1(features)))).permute(0, 2, 1) + embed_positions.weight
+ * with conv1 = Conv1d(80, 384, 3, padding=1) (:567) and conv2 = Conv1d(384, 384, 3, stride=2, padding=1) (:568), on the
+ * tensor cores: BF16 operands, FP32 accumulation, exact (erf) GELU, FP32 output.
+ *   features   [batch][80][3000] float32 (the output of b200mel_whisper_logmel_f32)
+ *   w1         [384][256] bfloat16: w1[co][tap * 80 + ci] = conv1.weight[co][ci][tap], columns 240..255 zero
+ *   w2         [384][1152] bfloat16: w2[co][tap * 384 + ci] = conv2.weight[co][ci][tap]
+ *   bias1, bias2   [384] float32;  positions  [1500][384] float32
+ *   out        [batch][1500][384] float32
+ *   workspace  b200mel_encoder_stem_workspace_bytes(h, batch) bytes (the BF16 im2col image of the features and the
+ *              BF16 activations between the convolutions); no initialisation needed.
+ * Every pointer 16-byte aligned.  Stream-ordered, no host synchronisation, CUDA-graph capturable. */
+size_t b200mel_encoder_stem_workspace_bytes(const b200mel_handle* h, int32_t batch);
+int b200mel_encoder_stem_bf16(b200mel_handle* h, const float* features, int32_t batch, const void* w1, const float* bias1,
+                              const void* w2, const float* bias2, const float* positions, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* (B, 3000) int32 frame mask: mask[b][t] = (160*t < min(lengths[b], 480000)). */
 int b200mel_whisper_frame_mask(b200mel_handle* h, const int32_t* lengths, int32_t batch,
                                int32_t* mask_out, void* stream);
