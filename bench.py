@@ -305,6 +305,64 @@ def urban_secondary(dev, peak_gbs: float) -> dict:
     return out
 
 
+def encoder_stem_secondary(dev, dev_pool, peak_tflops) -> dict:
+    """features + the tensor-core encoder stem (conv1 + GELU + conv2 + GELU +
+    positions of a seeded random-init whisper-tiny encoder) on the bench batch, next to the same lines run by
+    torch / cuDNN (HF:models/whisper/modeling_whisper.py:619-625) in FP32, TF32 and BF16."""
+    import torch
+    import transformers as tr
+    from audio_transformers_b200 import B200WhisperEncoderStem, ops
+    F = torch.nn.functional
+    torch.manual_seed(99)
+    enc = tr.WhisperModel(tr.WhisperConfig()).encoder.eval().to(dev)
+    stem = B200WhisperEncoderStem.from_encoder(enc).to(dev)
+    B = dev_pool[0].shape[0]
+    flops = B * (3000 * 384 * 240 + 1500 * 384 * 1152) * 2.0
+
+    def timed(fn, iters=20):
+        for _ in range(3):
+            fn(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    feats = [ops.whisper_logmel(x, None) for x in dev_pool[:2]]
+    out = {"batch": B, "flops_per_step": flops,
+           "note": "BF16 operands, FP32 accumulation in tensor memory (tcgen05.mma), exact GELU; parity in tests/test_encoder_stem_gpu.py"}
+    ms_stem = timed(lambda i: stem(feats[i % 2]))
+    ms_both = timed(lambda i: stem(ops.whisper_logmel(dev_pool[i % len(dev_pool)], None)))
+    out["stem_ms"] = ms_stem
+    out["stem_tflops"] = flops / (ms_stem * 1e-3) / 1e12
+    out["stem_frac_of_bf16_peak"] = out["stem_tflops"] / peak_tflops if peak_tflops else None
+    out["features_plus_stem_ms"] = ms_both
+    out["features_plus_stem_clips_per_s"] = B / (ms_both * 1e-3)
+
+    def lib_stem(x, dt):
+        with torch.no_grad():
+            y = F.gelu(F.conv1d(x.to(dt), enc.conv1.weight.to(dt), enc.conv1.bias.to(dt), padding=1))
+            y = F.gelu(F.conv1d(y, enc.conv2.weight.to(dt), enc.conv2.bias.to(dt), stride=2, padding=1))
+            return y.permute(0, 2, 1) + enc.embed_positions.weight.to(dt)
+    lib = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, dt, tf32 in (("fp32", torch.float32, False), ("tf32", torch.float32, True), ("bf16", torch.bfloat16, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            lib[name + "_ms"] = timed(lambda i: lib_stem(feats[i % 2], dt), iters=5)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["torch_cudnn_stem"] = lib
+    with torch.no_grad():
+        ref = lib_stem(feats[0], torch.float32)
+        got = stem(feats[0])
+    out["max_abs_vs_torch_fp32"] = float((got - ref).abs().max())
+    return out
+
+
 def run_ours(args) -> dict | None:
     import torch
     import torch.distributed as dist
@@ -511,6 +569,17 @@ def run_ours(args) -> dict | None:
             result["secondary"] = {"urban": urban_secondary(dev, peak)}
         except Exception as exc:  # pragma: no cover
             result["secondary"] = {"urban": {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}}
+        try:
+            tf = None
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    mp = json.load(f)
+                tf = next((float(v) for k, v in mp.items() if "tf" in k.lower() and isinstance(v, (int, float))), None)
+            except Exception:
+                pass
+            result["secondary"]["encoder_stem"] = encoder_stem_secondary(dev, dev_pool, tf)
+        except Exception as exc:  # pragma: no cover
+            result["secondary"]["encoder_stem"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     return result
 
 

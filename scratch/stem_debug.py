@@ -36,3 +36,17 @@ if len(sys.argv) > 2:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"B={B}: {ms*1e3:.1f} us per call, {B*1.88e9/ms/1e9:.1f} TFLOP/s")
+if len(sys.argv) > 3:
+    def lib_stem(x, dt):
+        with torch.no_grad():
+            y = F.gelu(F.conv1d(x.to(dt), enc.conv1.weight.to(dt), enc.conv1.bias.to(dt), padding=1))
+            y = F.gelu(F.conv1d(y, enc.conv2.weight.to(dt), enc.conv2.bias.to(dt), stride=2, padding=1))
+            return y.permute(0, 2, 1) + enc.embed_positions.weight.to(dt)
+    for dt, tf32 in ((torch.float32, False), (torch.float32, True), (torch.bfloat16, True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        for _ in range(3): lib_stem(feats, dt)
+        e0.record()
+        for _ in range(10): lib_stem(feats, dt)
+        e1.record(); torch.cuda.synchronize()
+        print(f"torch/cuDNN stem {dt} tf32={tf32}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per call")

@@ -25,8 +25,8 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             name = m.group(1)
-            short = re.search(r"\d+([a-z_0-9]+kernel[a-z_0-9]*)E", name)
-            cur = short.group(1) if short else name
+            short = re.search(r"win\d{3}\d\d([a-z_0-9]+kernel[a-z_0-9]*)(ILi(\d)E)?E", name)
+            cur = (short.group(1) + (f"<{short.group(3)}>" if short.group(3) else "")) if short else name
             kernels[cur] = []
             continue
         m = re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\w+\s+)?([A-Z][A-Z0-9_.]*)", line)
