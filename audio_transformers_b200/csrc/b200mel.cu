@@ -583,7 +583,6 @@ int b200mel_whisper_logmel_host(b200mel_handle* h, const void* const* clips, con
   }
   cudaStream_t stream = (cudaStream_t)stream_;
   cudaError_t first_err = cudaSuccess;
-  std::mutex err_mutex;
   cudaError_t e = cudaMemcpyAsync(dev_lengths, pinned_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync (lengths)");
   if (total > 0) {
@@ -597,35 +596,60 @@ int b200mel_whisper_logmel_host(b200mel_handle* h, const void* const* clips, con
     if (nt > npieces) nt = npieces;
     const int device = h->device;
     std::atomic<int> next_piece{0};
-    auto worker = [&](int) {
+    std::vector<std::atomic<unsigned char>> done((size_t)npieces);
+    for (auto& f : done) f.store(0, std::memory_order_relaxed);
+    // the valid samples of piece range [begin, end) of the flattened batch -> per-clip segments
+    auto for_segments = [&](int64_t begin, int64_t end, auto&& fn) {
+      int64_t pos = 0;
+      for (int i = 0; i < n && pos < end; ++i) {
+        const int64_t L = pinned_lengths[i];
+        const int64_t lo = begin > pos ? begin - pos : 0, hi = (end - pos) < L ? (end - pos) : L;
+        if (lo < hi) fn(i, lo, hi);
+        pos += L;
+      }
+    };
+    // Part 0 issues the copies, the other parts cast.  ONE thread makes every CUDA call, in order and for runs of
+    // finished pieces (up to 4 MB per copy): sixteen threads calling cudaMemcpyAsync for 0.5 MB each spent more time in
+    // the driver's lock than the copies took (the call cost 3.8 ms for 64 clips against 2.7 ms for the cast alone).
+    auto issuer = [&]() {
       int cur = -1;
       cudaGetDevice(&cur);
       if (cur != device) cudaSetDevice(device);
+      const int max_run = (int)(((int64_t)1 << 20) / per > 0 ? ((int64_t)1 << 20) / per : 1);
+      int p = 0;
+      while (p < npieces) {
+        while (!done[(size_t)p].load(std::memory_order_acquire)) {
+#if defined(__x86_64__)
+          __builtin_ia32_pause();
+#endif
+        }
+        int q = p + 1;
+        while (q < npieces && q - p < max_run && done[(size_t)q].load(std::memory_order_acquire)) ++q;
+        const int64_t begin = per * p, end = per * q < total ? per * q : total;
+        for_segments(begin, end, [&](int i, int64_t lo, int64_t hi) {
+          const size_t off = (size_t)i * (size_t)width + (size_t)lo;
+          const cudaError_t ce = cudaMemcpyAsync(dev_wave + off, pinned + off, (size_t)(hi - lo) * sizeof(float),
+                                                 cudaMemcpyHostToDevice, stream);
+          if (ce != cudaSuccess && first_err == cudaSuccess) first_err = ce;
+        });
+        p = q;
+      }
+    };
+    auto caster = [&]() {
       for (;;) {
         const int p = next_piece.fetch_add(1);
         if (p >= npieces) break;
         const int64_t begin = per * p, end = per * (p + 1) < total ? per * (p + 1) : total;
-        int64_t pos = 0;
-        for (int i = 0; i < n && pos < end; ++i) {
-          const int64_t L = pinned_lengths[i];
-          const int64_t lo = begin > pos ? begin - pos : 0, hi = (end - pos) < L ? (end - pos) : L;
-          if (lo < hi) {
-            float* d = pinned + (size_t)i * (size_t)width;
-            if (is_f64[i]) {
-              cast_f64_f32((const double*)clips[i] + lo, d + lo, hi - lo);
-            } else {
-              memcpy(d + lo, (const float*)clips[i] + lo, (size_t)(hi - lo) * sizeof(float));
-            }
-            const cudaError_t ce = cudaMemcpyAsync(dev_wave + (size_t)i * (size_t)width + lo, d + lo,
-                                                   (size_t)(hi - lo) * sizeof(float), cudaMemcpyHostToDevice, stream);
-            if (ce != cudaSuccess) { std::lock_guard<std::mutex> lk(err_mutex); if (first_err == cudaSuccess) first_err = ce; }
-          }
-          pos += L;
-        }
+        for_segments(begin, end, [&](int i, int64_t lo, int64_t hi) {
+          float* d = pinned + (size_t)i * (size_t)width;
+          if (is_f64[i]) cast_f64_f32((const double*)clips[i] + lo, d + lo, hi - lo);
+          else memcpy(d + lo, (const float*)clips[i] + lo, (size_t)(hi - lo) * sizeof(float));
+        });
+        done[(size_t)p].store(1, std::memory_order_release);
       }
     };
-    if (nt <= 1) worker(0);
-    else PackPool::get().run(nt, worker);
+    if (nt <= 1) { caster(); issuer(); }
+    else PackPool::get().run(nt + 1, [&](int part) { if (part == 0) issuer(); else caster(); });
     if (first_err != cudaSuccess) return fail_cuda(first_err, "cudaMemcpyAsync (audio piece)");
   }
   return b200mel_whisper_logmel_f32(h, dev_wave, width, dev_lengths, n, out, workspace, workspace_bytes, stream_);
