@@ -430,7 +430,8 @@ int b200mel_encoder_stem_bf16(b200mel_handle* h, const float* features, int32_t 
   EsGemm g1{batch, (ES_T + ES_BM - 1) / ES_BM, ES_T, ES_K1 / ES_BK, ES_K1 / ES_BK, bias1, nullptr, hid};
   EsGemm g2{batch, (ES_T2 + ES_BM - 1) / ES_BM, ES_T2, ES_K2 / ES_BK, ES_D / ES_BK, bias2, positions, out};
   const int t1 = batch * g1.mtiles * (ES_D / ES_BN), t2 = batch * g2.mtiles * (ES_D / ES_BN);
-  es_gemm_kernel<0><<<t1 < h->sm_count ? t1 : h->sm_count, ES_THREADS, ES_SMEM_BYTES, stream>>>(tm_a1, tm_w1, g1);
+  // conv1: a CTA keeps one channel half of W1 resident, so the grid is an even number of CTAs (half of them per channel half)
+  es_gemm_kernel<0><<<t1 < (h->sm_count & ~1) ? t1 : (h->sm_count & ~1), ES_THREADS, ES_SMEM_BYTES, stream>>>(tm_a1, tm_w1, g1);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "es_gemm_kernel<conv1> launch");
   es_gemm_kernel<1><<<t2 < h->sm_count ? t2 : h->sm_count, ES_THREADS, ES_SMEM_BYTES, stream>>>(tm_h, tm_w2, g2);

@@ -33,7 +33,7 @@ constexpr int ES_STAGES = 4;
 constexpr int ES_A_BYTES = ES_BM * ES_BK * 2, ES_B_BYTES = ES_BN * ES_BK * 2, ES_STAGE_BYTES = ES_A_BYTES + ES_B_BYTES;
 constexpr int ES_THREADS = 320, ES_EPI_WARPS = 8;
 constexpr int ES_ACC_COLS = 256, ES_TMEM_COLS = 512;     // two accumulators, 192 columns used of each 256
-constexpr int ES_SMEM_BYTES = ES_STAGES * ES_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers, tmem address */;
+constexpr int ES_SMEM_BYTES = ES_STAGES * ES_STAGE_BYTES + 8 * 4096 /* epilogue staging */ + 1024 /* alignment slack */ + 256 /* barriers, tmem address */;
 static_assert(ES_A_BYTES % 1024 == 0 && ES_B_BYTES % 1024 == 0, "swizzle atoms are 1024-byte aligned");
 static_assert(ES_D % ES_BN == 0 && ES_K1 % ES_BK == 0 && ES_K2 % ES_BK == 0 && ES_D % ES_BK == 0, "tiling");
 
@@ -170,25 +170,52 @@ struct EsGemm {
   void* out;          // conv1: h, BF16 [batch][3002][384]; conv2: FP32 [batch][1500][384]
 };
 
+// Shared memory.  conv2 (MODE 1): a ring of ES_STAGES x {A 16 KB, W 24 KB}.  conv1 (MODE 0): K is only four blocks, so the
+// CTA keeps its channel half of W1 (4 x 24 KB) resident for the whole kernel and the ring holds A tiles only.  Then one
+// staging buffer per epilogue warp (a 32 x 32 chunk of the output: rows leave as full 128-byte / 64-byte segments), the
+// mbarriers and the tensor-memory address.
+constexpr int ES_RING1 = ES_STAGES * ES_STAGE_BYTES;                         // MODE 1
+constexpr int ES_W1_BYTES = (ES_K1 / ES_BK) * ES_B_BYTES;                    // MODE 0: resident W1 half, 96 KB
+constexpr int ES_RING0 = ES_W1_BYTES + ES_STAGES * ES_A_BYTES;
+constexpr int ES_STG_OFF = ES_RING1 > ES_RING0 ? ES_RING1 : ES_RING0;
+constexpr int ES_STG_BYTES = 32 * 32 * 4;
+constexpr int ES_BAR_OFF = ES_STG_OFF + ES_EPI_WARPS * ES_STG_BYTES;
+static_assert(ES_BAR_OFF + 256 + 1024 <= ES_SMEM_BYTES, "shared-memory budget of es_gemm_kernel");
+
 template <int MODE>   // 0: conv1 -> h (BF16), 1: conv2 -> hidden states (FP32, + positions)
 __global__ void __launch_bounds__(ES_THREADS, 1)
 es_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const EsGemm p) {
   extern __shared__ unsigned char es_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)es_smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + ES_STAGES * ES_STAGE_BYTES);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + ES_BAR_OFF);
   unsigned long long* full = bars;                         // [ES_STAGES] TMA -> MMA
   unsigned long long* empty = bars + ES_STAGES;            // [ES_STAGES] MMA -> TMA
   unsigned long long* acc_full = bars + 2 * ES_STAGES;     // [2] MMA -> epilogue
   unsigned long long* acc_empty = bars + 2 * ES_STAGES + 2;   // [2] epilogue -> MMA
-  unsigned* s_tmem = reinterpret_cast<unsigned*>(bars + 2 * ES_STAGES + 4);
+  unsigned long long* w_full = bars + 2 * ES_STAGES + 4;   // MODE 0: the resident W1 half has landed
+  unsigned* s_tmem = reinterpret_cast<unsigned*>(bars + 2 * ES_STAGES + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntiles = p.batch * p.mtiles * (ES_D / ES_BN);
+  // MODE 1: tiles (clip, 128 rows, channel half) round robin over the CTAs, the two halves of a row block side by side.
+  // MODE 0: the CTA's channel half is fixed (blockIdx & 1; the grid is even) and it walks row blocks only.
+  constexpr int NH = ES_D / ES_BN;
+  const int t_first = MODE == 0 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = MODE == 0 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int t_count = MODE == 0 ? p.batch * p.mtiles : p.batch * p.mtiles * NH;
+  auto decode = [&](int it, int& nt, int& mt, int& clip) {
+    const int lin = MODE == 0 ? it : it / NH;
+    nt = MODE == 0 ? (int)(blockIdx.x & 1) : it - lin * NH;
+    clip = lin / p.mtiles;
+    mt = lin - clip * p.mtiles;
+  };
+  constexpr int A_STRIDE = MODE == 0 ? ES_A_BYTES : ES_STAGE_BYTES;          // distance between ring slots
+  unsigned char* ring = smem + (MODE == 0 ? ES_W1_BYTES : 0);
 
   if (warp == 0 && lane == 0) {
     es_prefetch_tmap(&tm_a);
     es_prefetch_tmap(&tm_w);
     for (int i = 0; i < ES_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, ES_EPI_WARPS); }
+    mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -207,16 +234,22 @@ es_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      if (MODE == 0) {                                  // weights first: they do not depend on the previous kernel's output
+        mbar_arrive_expect_tx(w_full, ES_W1_BYTES);
+        for (int kb = 0; kb < ES_K1 / ES_BK; ++kb)
+          es_tma_load_2d(smem + kb * ES_B_BYTES, &tm_w, kb * ES_BK, (int)(blockIdx.x & 1) * ES_BN, w_full);
+      }
       int stage = 0; unsigned phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int nt = tile % (ES_D / ES_BN), mt = (tile / (ES_D / ES_BN)) % p.mtiles, clip = tile / ((ES_D / ES_BN) * p.mtiles);
+      for (int it = t_first; it < t_count; it += t_step) {
+        int nt, mt, clip;
+        decode(it, nt, mt, clip);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty + stage, phase ^ 1u);
-          unsigned char* sa = smem + stage * ES_STAGE_BYTES;
-          mbar_arrive_expect_tx(full + stage, ES_STAGE_BYTES);
+          unsigned char* sa = ring + stage * A_STRIDE;
+          mbar_arrive_expect_tx(full + stage, MODE == 0 ? ES_A_BYTES : ES_STAGE_BYTES);
           const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * ES_BK;
           es_tma_load_4d(sa, &tm_a, c0, tap & 1, mt * ES_BM + (tap >> 1), clip, full + stage);
-          es_tma_load_2d(sa + ES_A_BYTES, &tm_w, kb * ES_BK, nt * ES_BN, full + stage);
+          if (MODE == 1) es_tma_load_2d(sa + ES_A_BYTES, &tm_w, kb * ES_BK, nt * ES_BN, full + stage);
           if (++stage == ES_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -225,7 +258,8 @@ es_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ===== MMA issuer =====
     int stage = 0; unsigned phase = 0;
     int acc = 0; unsigned acc_phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (MODE == 0) mbar_wait(w_full, 0);
+    for (int it = t_first; it < t_count; it += t_step) {
       mbar_wait(acc_empty + acc, acc_phase ^ 1u);
       es_tc_fence_after();
       const unsigned d_tmem = tmem_base + (unsigned)(acc * ES_ACC_COLS);
@@ -233,8 +267,9 @@ es_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         mbar_wait(full + stage, phase);
         es_tc_fence_after();
         if (lane == 0) {
-          const unsigned sa = smem_u32(smem + stage * ES_STAGE_BYTES);
-          const unsigned long long adesc = es_smem_desc(sa), bdesc = es_smem_desc(sa + ES_A_BYTES);
+          const unsigned sa = smem_u32(ring + stage * A_STRIDE);
+          const unsigned sb = MODE == 0 ? smem_u32(smem + kb * ES_B_BYTES) : sa + ES_A_BYTES;
+          const unsigned long long adesc = es_smem_desc(sa), bdesc = es_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < ES_BK / ES_UK; ++k)     // 32 bytes further along K inside the swizzle atom: + 2 in the address field
             es_umma(d_tmem, adesc + 2u * k, bdesc + 2u * k, (kb | k) != 0);
@@ -249,11 +284,17 @@ es_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else {
     // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31, columns 96 ((w - 2) / 4) .. + 95 of the accumulator =====
+    // A lane owns a ROW of the accumulator; rows are 768 / 1536 bytes apart in memory, so a chunk of 32 rows x 32 columns
+    // goes through the warp's staging buffer (16-byte slots, XOR-swizzled so that neither side has bank conflicts) and
+    // leaves with a quarter-warp (conv2) / four lanes (conv1) per row: full 128-byte / 64-byte segments, and the
+    // positional embedding is read the same way.
     const int q = warp & 3, half = (warp - 2) >> 2;
+    unsigned char* stg = smem + ES_STG_OFF + (warp - 2) * ES_STG_BYTES;
     int acc = 0; unsigned acc_phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int nt = tile % (ES_D / ES_BN), mt = (tile / (ES_D / ES_BN)) % p.mtiles, clip = tile / ((ES_D / ES_BN) * p.mtiles);
-      const int m = mt * ES_BM + q * 32 + lane;
+    for (int it = t_first; it < t_count; it += t_step) {
+      int nt, mt, clip;
+      decode(it, nt, mt, clip);
+      const int m0 = mt * ES_BM + q * 32;                      // first row of this warp's chunk
       mbar_wait(acc_full + acc, acc_phase);
       es_tc_fence_after();
 #pragma unroll 1
@@ -266,35 +307,53 @@ es_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           __syncwarp();
           if (lane == 0) es_mbar_arrive(acc_empty + acc);
         }
-        if (m < p.m_valid) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-          if (MODE == 0) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ((size_t)clip * ES_HROWS + 1 + m) * ES_D + n0);
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+        if (MODE == 0) {
+          uint4* s4 = reinterpret_cast<uint4*>(stg);            // [32 rows][4 slots of 8 BF16]
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
-              const float2 g0 = es_gelu2(__fadd2_rn(make_float2(v[8 * g], v[8 * g + 1]), make_float2(ba.x, ba.y)));
-              const float2 g1 = es_gelu2(__fadd2_rn(make_float2(v[8 * g + 2], v[8 * g + 3]), make_float2(ba.z, ba.w)));
-              const float2 g2 = es_gelu2(__fadd2_rn(make_float2(v[8 * g + 4], v[8 * g + 5]), make_float2(bb.x, bb.y)));
-              const float2 g3 = es_gelu2(__fadd2_rn(make_float2(v[8 * g + 6], v[8 * g + 7]), make_float2(bb.z, bb.w)));
-              __nv_bfloat162 o0 = __floats2bfloat162_rn(g0.x, g0.y), o1 = __floats2bfloat162_rn(g1.x, g1.y);
-              __nv_bfloat162 o2 = __floats2bfloat162_rn(g2.x, g2.y), o3 = __floats2bfloat162_rn(g3.x, g3.y);
-              uint4 o;
-              o.x = *reinterpret_cast<unsigned*>(&o0); o.y = *reinterpret_cast<unsigned*>(&o1);
-              o.z = *reinterpret_cast<unsigned*>(&o2); o.w = *reinterpret_cast<unsigned*>(&o3);
-              dst[g] = o;
-            }
-          } else {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((size_t)clip * ES_T2 + m) * ES_D + n0);
-            const float4* pos4 = reinterpret_cast<const float4*>(p.pos + (size_t)m * ES_D + n0);
+          for (int g = 0; g < 4; ++g) {
+            const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
+            const float2 g0 = es_gelu2(__fadd2_rn(make_float2(v[8 * g], v[8 * g + 1]), make_float2(ba.x, ba.y)));
+            const float2 g1 = es_gelu2(__fadd2_rn(make_float2(v[8 * g + 2], v[8 * g + 3]), make_float2(ba.z, ba.w)));
+            const float2 g2 = es_gelu2(__fadd2_rn(make_float2(v[8 * g + 4], v[8 * g + 5]), make_float2(bb.x, bb.y)));
+            const float2 g3 = es_gelu2(__fadd2_rn(make_float2(v[8 * g + 6], v[8 * g + 7]), make_float2(bb.z, bb.w)));
+            __nv_bfloat162 o0 = __floats2bfloat162_rn(g0.x, g0.y), o1 = __floats2bfloat162_rn(g1.x, g1.y);
+            __nv_bfloat162 o2 = __floats2bfloat162_rn(g2.x, g2.y), o3 = __floats2bfloat162_rn(g3.x, g3.y);
+            uint4 o;
+            o.x = *reinterpret_cast<unsigned*>(&o0); o.y = *reinterpret_cast<unsigned*>(&o1);
+            o.z = *reinterpret_cast<unsigned*>(&o2); o.w = *reinterpret_cast<unsigned*>(&o3);
+            s4[lane * 4 + (g ^ ((lane >> 1) & 3))] = o;
+          }
+          __syncwarp();
+          __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(p.out) + ((size_t)clip * ES_HROWS + 1) * ES_D + n0;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 b = __ldg(b4 + g), e = __ldg(pos4 + g);
-              const float2 g0 = __fadd2_rn(es_gelu2(__fadd2_rn(make_float2(v[4 * g], v[4 * g + 1]), make_float2(b.x, b.y))), make_float2(e.x, e.y));
-              const float2 g1 = __fadd2_rn(es_gelu2(__fadd2_rn(make_float2(v[4 * g + 2], v[4 * g + 3]), make_float2(b.z, b.w))), make_float2(e.z, e.w));
-              dst[g] = make_float4(g0.x, g0.y, g1.x, g1.y);
+          for (int r8 = 0; r8 < 4; ++r8) {
+            const int row = r8 * 8 + (lane >> 2), j = lane & 3;
+            const uint4 o = s4[row * 4 + (j ^ ((row >> 1) & 3))];
+            if (m0 + row < p.m_valid) reinterpret_cast<uint4*>(hb + (size_t)(m0 + row) * ES_D)[j] = o;
+          }
+          __syncwarp();
+        } else {
+          float4* s4 = reinterpret_cast<float4*>(stg);          // [32 rows][8 slots of 4 floats]
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b = __ldg(b4 + g);
+            const float2 g0 = es_gelu2(__fadd2_rn(make_float2(v[4 * g], v[4 * g + 1]), make_float2(b.x, b.y)));
+            const float2 g1 = es_gelu2(__fadd2_rn(make_float2(v[4 * g + 2], v[4 * g + 3]), make_float2(b.z, b.w)));
+            s4[lane * 8 + (g ^ (lane & 7))] = make_float4(g0.x, g0.y, g1.x, g1.y);
+          }
+          __syncwarp();
+          float* ob = reinterpret_cast<float*>(p.out) + (size_t)clip * ES_T2 * ES_D + n0;
+#pragma unroll
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int row = r4 * 4 + (lane >> 3), j = lane & 7;
+            const float4 o = s4[row * 8 + (j ^ (row & 7))];
+            if (m0 + row < p.m_valid) {
+              const float4 e = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(m0 + row) * ES_D + n0) + j);
+              reinterpret_cast<float4*>(ob + (size_t)(m0 + row) * ES_D)[j] = make_float4(o.x + e.x, o.y + e.y, o.z + e.z, o.w + e.w);
             }
           }
+          __syncwarp();
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }

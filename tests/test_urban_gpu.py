@@ -70,6 +70,27 @@ def test_lengths(ops, n):
     assert np.abs(out[1][strong] - np.log(lin64[strong] + 1e-9)).max() <= TOL
 
 
+def test_pure_tone_weak_bins_against_live_torchaudio(ops):
+    """The carve-out of test_lengths with numbers next to it: on the bins it excludes (mel below 1e-4 of the clip's peak
+    for a pure tone) the log-mel of the CUDA path, of live torchaudio on this host's CPU and of the FP64 restatement are
+    compared pairwise.  torchaudio itself misses FP64 there by more than the contract tolerance; the CUDA path must be
+    no further from FP64 than a small multiple of that."""
+    ta = pytest.importorskip("torchaudio")
+    n = 88200
+    wave = (0.5 * np.sin(2 * np.pi * 1000.0 * np.arange(n) / 22050.0)).astype(np.float32)[None]
+    ours = ops.mel_power(torch.from_numpy(wave).cuda(), 1e-9).cpu().numpy()[0]
+    lib = torch.log(ta.transforms.MelSpectrogram(sample_rate=22050, n_fft=1024, hop_length=512, n_mels=64)(torch.from_numpy(wave)) + 1e-9).numpy()[0]
+    lin64 = O.urban_melspec(wave, log_eps=None, dtype=np.float64)[0]
+    truth = np.log(lin64 + 1e-9)
+    weak = lin64 <= 1e-4 * lin64.max()
+    assert weak.any() and (~weak).any()
+    e_ours, e_lib, e_pair = (float(np.abs(a[weak] - b[weak]).max()) for a, b in ((ours, truth), (lib, truth), (ours, lib)))
+    print(f"pure tone, {int(weak.sum())} weak bins of {weak.size}: |cuda - fp64| {e_ours:.2e}  |torchaudio cpu - fp64| {e_lib:.2e}  "
+          f"|cuda - torchaudio cpu| {e_pair:.2e};  strong bins: |cuda - torchaudio cpu| {float(np.abs(ours[~weak] - lib[~weak]).max()):.2e}")
+    assert np.abs(ours[~weak] - lib[~weak]).max() <= TOL
+    assert e_ours <= max(4.0 * e_lib, TOL)
+
+
 def test_module_matches_live_torchaudio(ops):
     ta = pytest.importorskip("torchaudio")
     from audio_transformers_b200 import B200MelSpectrogram
