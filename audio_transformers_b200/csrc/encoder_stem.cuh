@@ -18,7 +18,7 @@
 //           stride-2 rows of a tap as one box.
 // A CTA owns 128 (time) x 192 (channel) output tiles.  Warp 0: TMA producer (one lane) through a 4-stage ring of
 // {A 128 x 64, W 192 x 64} BF16 tiles in the 128-byte-swizzled K-major layout; warp 1: tensor-memory allocation and the
-// single thread that issues tcgen05.mma (M 128, N 192, K 16) and commits to mbarriers; warps 2..9: epilogue
+// single thread that issues tcgen05.mma (M 128, N 192, K 16) and commits to mbarriers; warps 2..13: epilogue
 // (tcgen05.ld, bias, exact GELU, conv1: BF16 rows of h; conv2: + positional embedding, FP32 rows of the output).  Two
 // accumulators of 192 columns alternate, so the epilogue of a tile runs under the MMAs of the next one.
 // ================================================================================================
@@ -31,9 +31,9 @@ constexpr int ES_HROWS = ES_T + 2;               // rows of h per clip: a zero r
 constexpr int ES_BM = 128, ES_BN = 192, ES_BK = 64, ES_UK = 16;
 constexpr int ES_STAGES = 4;
 constexpr int ES_A_BYTES = ES_BM * ES_BK * 2, ES_B_BYTES = ES_BN * ES_BK * 2, ES_STAGE_BYTES = ES_A_BYTES + ES_B_BYTES;
-constexpr int ES_THREADS = 320, ES_EPI_WARPS = 8;
+constexpr int ES_EPI_WARPS = 12, ES_THREADS = (2 + ES_EPI_WARPS) * 32;   // three epilogue warps per TMEM lane quarter, two 32-column chunks each
 constexpr int ES_ACC_COLS = 256, ES_TMEM_COLS = 512;     // two accumulators, 192 columns used of each 256
-constexpr int ES_SMEM_BYTES = ES_STAGES * ES_STAGE_BYTES + 8 * 4096 /* epilogue staging */ + 1024 /* alignment slack */ + 256 /* barriers, tmem address */;
+constexpr int ES_SMEM_BYTES = ES_STAGES * ES_STAGE_BYTES + ES_EPI_WARPS * 4096 /* epilogue staging */ + 1024 /* alignment slack */ + 256 /* barriers, tmem address */;
 static_assert(ES_A_BYTES % 1024 == 0 && ES_B_BYTES % 1024 == 0, "swizzle atoms are 1024-byte aligned");
 static_assert(ES_D % ES_BN == 0 && ES_K1 % ES_BK == 0 && ES_K2 % ES_BK == 0 && ES_D % ES_BK == 0, "tiling");
 
@@ -283,12 +283,12 @@ es_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
-    // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31, columns 96 ((w - 2) / 4) .. + 95 of the accumulator =====
+    // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31, columns 64 ((w - 2) / 4) .. + 63 of the accumulator =====
     // A lane owns a ROW of the accumulator; rows are 768 / 1536 bytes apart in memory, so a chunk of 32 rows x 32 columns
     // goes through the warp's staging buffer (16-byte slots, XOR-swizzled so that neither side has bank conflicts) and
     // leaves with a quarter-warp (conv2) / four lanes (conv1) per row: full 128-byte / 64-byte segments, and the
     // positional embedding is read the same way.
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, part = (warp - 2) >> 2;
     unsigned char* stg = smem + ES_STG_OFF + (warp - 2) * ES_STG_BYTES;
     int acc = 0; unsigned acc_phase = 0;
     for (int it = t_first; it < t_count; it += t_step) {
@@ -298,11 +298,11 @@ es_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_wait(acc_full + acc, acc_phase);
       es_tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        const int col = half * 96 + c * 32, n0 = nt * ES_BN + col;
+      for (int c = 0; c < 2; ++c) {
+        const int col = part * 64 + c * 32, n0 = nt * ES_BN + col;
         float v[32];
         es_tmem_ld32(tmem_base + (unsigned)(acc * ES_ACC_COLS + col) + ((unsigned)(q * 32) << 16), v);
-        if (c == 2) {                               // the accumulator is in registers: hand it back to the MMA warp
+        if (c == 1) {                               // the accumulator is in registers: hand it back to the MMA warp
           es_tc_fence_before();
           __syncwarp();
           if (lane == 0) es_mbar_arrive(acc_empty + acc);
