@@ -609,34 +609,41 @@ int b200mel_whisper_logmel_host(b200mel_handle* h, const void* const* clips, con
         pos += L;
       }
     };
-    // Part 0 issues the copies, the other parts cast.  ONE thread makes every CUDA call, in order and for runs of
-    // finished pieces (up to 4 MB per copy): sixteen threads calling cudaMemcpyAsync for 0.5 MB each spent more time in
-    // the driver's lock than the copies took (the call cost 3.8 ms for 64 clips against 2.7 ms for the cast alone).
-    auto issuer = [&]() {
-      int cur = -1;
-      cudaGetDevice(&cur);
-      if (cur != device) cudaSetDevice(device);
-      const int max_run = (int)(((int64_t)1 << 20) / per > 0 ? ((int64_t)1 << 20) / per : 1);
-      int p = 0;
-      while (p < npieces) {
-        while (!done[(size_t)p].load(std::memory_order_acquire)) {
-#if defined(__x86_64__)
-          __builtin_ia32_pause();
-#endif
-        }
-        int q = p + 1;
-        while (q < npieces && q - p < max_run && done[(size_t)q].load(std::memory_order_acquire)) ++q;
-        const int64_t begin = per * p, end = per * q < total ? per * q : total;
-        for_segments(begin, end, [&](int i, int64_t lo, int64_t hi) {
-          const size_t off = (size_t)i * (size_t)width + (size_t)lo;
-          const cudaError_t ce = cudaMemcpyAsync(dev_wave + off, pinned + off, (size_t)(hi - lo) * sizeof(float),
-                                                 cudaMemcpyHostToDevice, stream);
-          if (ce != cudaSuccess && first_err == cudaSuccess) first_err = ce;
-        });
-        p = q;
+    // Every part casts pieces; part 0 also issues the copies, between its own pieces and at the end: ONE thread makes
+    // every CUDA call, in order and for runs of finished pieces (up to 4 MB per copy).  Sixteen threads calling
+    // cudaMemcpyAsync for 0.5 MB each spent more time in the driver's lock than the copies took (the call cost 3.8 ms for
+    // 64 clips against 2.7 ms for the cast alone); a thread that only issued would burn a core the cast can use (with
+    // eight ranks on a 32-core host every rank has four).
+    const int max_run = (int)(((int64_t)1 << 20) / per > 0 ? ((int64_t)1 << 20) / per : 1);
+    auto work = [&](int part) {
+      const bool issuer = part == 0;
+      int p_issue = 0;
+      if (issuer) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
       }
-    };
-    auto caster = [&]() {
+      auto issue = [&](bool drain) {
+        while (p_issue < npieces) {
+          if (!done[(size_t)p_issue].load(std::memory_order_acquire)) {
+            if (!drain) return;
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            continue;
+          }
+          int q = p_issue + 1;
+          while (q < npieces && q - p_issue < max_run && done[(size_t)q].load(std::memory_order_acquire)) ++q;
+          const int64_t begin = per * p_issue, end = per * q < total ? per * q : total;
+          for_segments(begin, end, [&](int i, int64_t lo, int64_t hi) {
+            const size_t off = (size_t)i * (size_t)width + (size_t)lo;
+            const cudaError_t ce = cudaMemcpyAsync(dev_wave + off, pinned + off, (size_t)(hi - lo) * sizeof(float),
+                                                   cudaMemcpyHostToDevice, stream);
+            if (ce != cudaSuccess && first_err == cudaSuccess) first_err = ce;
+          });
+          p_issue = q;
+        }
+      };
       for (;;) {
         const int p = next_piece.fetch_add(1);
         if (p >= npieces) break;
@@ -647,10 +654,12 @@ int b200mel_whisper_logmel_host(b200mel_handle* h, const void* const* clips, con
           else memcpy(d + lo, (const float*)clips[i] + lo, (size_t)(hi - lo) * sizeof(float));
         });
         done[(size_t)p].store(1, std::memory_order_release);
+        if (issuer) issue(false);
       }
+      if (issuer) issue(true);
     };
-    if (nt <= 1) { caster(); issuer(); }
-    else PackPool::get().run(nt + 1, [&](int part) { if (part == 0) issuer(); else caster(); });
+    if (nt <= 1) work(0);
+    else PackPool::get().run(nt, work);
     if (first_err != cudaSuccess) return fail_cuda(first_err, "cudaMemcpyAsync (audio piece)");
   }
   return b200mel_whisper_logmel_f32(h, dev_wave, width, dev_lengths, n, out, workspace, workspace_bytes, stream_);
