@@ -298,8 +298,8 @@ int b200mel_profile_end(b200mel_handle* h, double* total_ms, int32_t* launches) 
 size_t b200mel_workspace_bytes(const b200mel_handle* h, int32_t batch) {
   if (!h || batch <= 0) return 0;
   if (h->preset != B200MEL_PRESET_WHISPER) return 0;
-  // 32-frame kernel: one float per (clip, tile, warp); 64-frame kernel: one word per clip
-  return ((size_t)batch * V_SLOTS_PER_CLIP * sizeof(float) + 255) & ~(size_t)255;
+  // one {max, min} pair per (clip, tile, warp)
+  return ((size_t)batch * V_SLOTS_PER_CLIP * sizeof(float2) + 255) & ~(size_t)255;
 }
 
 int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t stride_samples,
@@ -351,12 +351,12 @@ int b200mel_whisper_logmel_f32(b200mel_handle* h, const float* wave, int64_t str
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, whisper_logmel_kernel32, tmap, use_tma, wave, (long long)stride_samples, lengths,
-                                     (int)batch, out, (float*)workspace);
+                                     (int)batch, out, (float2*)workspace);
   if (e != cudaSuccess) return fail_cuda(e, "whisper_logmel_kernel32 launch");
   if (prof) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream); ++h->prof_n; }
   const int items = batch * CL_PARTS;
   const int grid = items < CL_CTAS_PER_SM * h->sm_count ? items : CL_CTAS_PER_SM * h->sm_count;
-  whisper_clamp_kernel32<<<grid, CL_THREADS, 0, stream>>>(out, (const float*)workspace, batch, lengths, (long long)stride_samples);
+  whisper_clamp_kernel32<<<grid, CL_THREADS, 0, stream>>>(out, (const float2*)workspace, batch, lengths, (long long)stride_samples);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "whisper_clamp_kernel32 launch");
   return B200MEL_OK;

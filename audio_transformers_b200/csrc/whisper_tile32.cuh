@@ -65,19 +65,20 @@ __device__ __forceinline__ float v_norm_log(float e_scaled) {
   return l * 0.07525749891599529f;
 }
 
-// Workspace of this kernel: one float per (clip, tile, warp) = the largest mel energy that warp saw in that tile.
-// Every slot is written exactly once per launch, so the workspace needs no zeroing (no memset node, no atomics),
-// and the clip-floor pass reduces a clip's 94 x 8 slots itself.
+// Workspace of this kernel: one float2 per (clip, tile, warp) = {largest, smallest} mel energy that warp saw in that
+// tile.  Every slot is written exactly once per launch, so the workspace needs no zeroing (no memset node, no atomics);
+// the clip-floor pass reduces a clip's 94 x 8 slots itself: the maximum gives the floor, and a clip whose minimum is
+// not below it has nothing to clamp and is not read at all.
 constexpr int V_SLOTS_PER_CLIP = V_TILES_PER_CLIP * V_WARPS;
-__device__ __forceinline__ float* v_slot(float* __restrict__ tile_max, int clip, int f0, int warp) {
+__device__ __forceinline__ float2* v_slot(float2* __restrict__ tile_max, int clip, int f0, int warp) {
   return tile_max + (size_t)clip * V_SLOTS_PER_CLIP + (f0 / V_TILE) * V_WARPS + warp;
 }
 
 // A tile of pure zero padding: its features are written by the floor pass; here only its maximum (mel = 0 ->
 // max(., 1e-10)) is recorded so that an all-silent clip still has a defined clip maximum.  Called by ONE thread.
-__device__ __forceinline__ void v_record_silent(const WTile& t, float* __restrict__ tile_max) {
+__device__ __forceinline__ void v_record_silent(const WTile& t, float2* __restrict__ tile_max) {
 #pragma unroll
-  for (int w = 0; w < V_WARPS; ++w) *v_slot(tile_max, t.clip, t.f0, w) = V_EFLOOR;
+  for (int w = 0; w < V_WARPS; ++w) *v_slot(tile_max, t.clip, t.f0, w) = make_float2(V_EFLOOR, V_EFLOOR);
 }
 
 __device__ __forceinline__ void v_stage_generic(const WTile& t, float* __restrict__ s_audio, int part, int nparts, int lane) {
@@ -158,21 +159,22 @@ __device__ __forceinline__ void v_mel_taps(const float (&pb)[NB], float& acc) {
 }
 
 template <int M, int FE, int BLO, int NB>
-__device__ __forceinline__ void v_mel_filters(const float (&pb)[NB], float* __restrict__ out_col, bool valid, float& emax) {
+__device__ __forceinline__ void v_mel_filters(const float (&pb)[NB], float* __restrict__ out_col, bool valid, float& emax, float& emin) {
   if constexpr (M < FE) {
     float acc;
     v_mel_taps<0, w_mel_len(M), w_mel_off(M), w_mel_start(M) - BLO, NB>(pb, acc);
     // No clamp at the reference's 1e-10 floor here: the floor pass raises every value to max(clip max - 8 decades,
     // floor) anyway (an exact zero gives -inf for the moment).  Lanes past frame 3000 are masked once, in v_mel_phase.
     emax = fmaxf(emax, acc);
+    emin = fminf(emin, acc);
     const float y = v_norm_log(acc);
     if (valid) out_col[(size_t)M * W_NFRAME] = y;
-    v_mel_filters<M + 1, FE, BLO, NB>(pb, out_col, valid, emax);
+    v_mel_filters<M + 1, FE, BLO, NB>(pb, out_col, valid, emax, emin);
   }
 }
 
 template <int S, int NS>
-__device__ __forceinline__ void v_mel_share(const float* __restrict__ p_lane, float* __restrict__ out_col, bool valid, float& emax) {
+__device__ __forceinline__ void v_mel_share(const float* __restrict__ p_lane, float* __restrict__ out_col, bool valid, float& emax, float& emin) {
   constexpr int FB = w_mel_first(S, NS), FE = w_mel_first(S + 1, NS);
   static_assert(FE > FB, "every share needs at least one filter");
   constexpr int BLO = w_mel_start(FB), BHI = w_mel_start(FE - 1) + w_mel_len(FE - 1);
@@ -180,25 +182,26 @@ __device__ __forceinline__ void v_mel_share(const float* __restrict__ p_lane, fl
   float pb[NB];
 #pragma unroll
   for (int k = 0; k < NB; ++k) pb[k] = p_lane[w_bin_row(BLO + k) * (2 * V_COLS)];
-  v_mel_filters<FB, FE, BLO, NB>(pb, out_col, valid, emax);
+  v_mel_filters<FB, FE, BLO, NB>(pb, out_col, valid, emax, emin);
 }
 
 __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0, const float2* __restrict__ s_p,
-                                            float* __restrict__ out, float* __restrict__ tile_max) {
+                                            float* __restrict__ out, float2* __restrict__ tile_max) {
   // lane l < 16: first frame of column l; lane l >= 16: second frame (8 frames later) of column l - 16
   const int col = lane & 15, half = lane >> 4;
   const int frame = f0 + 16 * (col >> 3) + (col & 7) + 8 * half;
   const bool valid = frame < W_NFRAME;
   const float* pl = reinterpret_cast<const float*>(s_p) + 2 * col + half;
   float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame;
-  float emax = 0.0f;
-#define V_MEL_CASE(w) case w: v_mel_share<2 * w, 16>(pl, out_col, valid, emax); v_mel_share<2 * w + 1, 16>(pl, out_col, valid, emax); break;
+  float emax = 0.0f, emin = 3.0e38f;
+#define V_MEL_CASE(w) case w: v_mel_share<2 * w, 16>(pl, out_col, valid, emax, emin); v_mel_share<2 * w + 1, 16>(pl, out_col, valid, emax, emin); break;
   switch (warp) { V_MEL_CASE(0) V_MEL_CASE(1) V_MEL_CASE(2) V_MEL_CASE(3) V_MEL_CASE(4) V_MEL_CASE(5) V_MEL_CASE(6) default: V_MEL_CASE(7) }
 #undef V_MEL_CASE
-  if (!valid) emax = 0.0f;
-  // energies are >= +0, so their bit patterns order like the values: one REDUX instead of five shuffle/max rounds
+  if (!valid) { emax = 0.0f; emin = 3.0e38f; }
+  // energies are >= +0, so their bit patterns order like the values: one REDUX each instead of five shuffle rounds
   emax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(emax)));
-  if (lane == 0) *v_slot(tile_max, clip, f0, warp) = emax;
+  emin = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(emin)));
+  if (lane == 0) *v_slot(tile_max, clip, f0, warp) = make_float2(emax, emin);
 }
 
 #ifndef V_L2_PREFETCH
@@ -221,7 +224,7 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
 template <int DUMMY>
 __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, const float* __restrict__ wave, long long stride,
                                       const int* __restrict__ lengths, int batch, float* __restrict__ out,
-                                      float* __restrict__ tile_max, float* smem) {
+                                      float2* __restrict__ tile_max, float* smem) {
   const int half = threadIdx.x >> 8, tid = threadIdx.x & (V_HALF_THREADS - 1), lane = tid & 31, warp = tid >> 5;
   float* s_audio = smem + half * V_HALF_FLOATS;
   float2* s_e = reinterpret_cast<float2*>(s_audio + V_SM_AUDIO);
@@ -327,7 +330,7 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
 __global__ void __launch_bounds__(V_THREADS, 1)
 whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
                         const float* __restrict__ wave, long long stride, const int* __restrict__ lengths,
-                        int batch, float* __restrict__ out, float* __restrict__ tile_max) {
+                        int batch, float* __restrict__ out, float2* __restrict__ tile_max) {
   extern __shared__ __align__(1024) float smem[];
   {
     int* s_off = reinterpret_cast<int*>(smem + V_HALVES * V_HALF_FLOATS);

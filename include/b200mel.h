@@ -81,8 +81,8 @@ const char* b200mel_last_error(void);
 int b200mel_create(int device, int preset, b200mel_handle** out);
 int b200mel_destroy(b200mel_handle* h);
 
-/* Bytes of device workspace a call with `batch` clips needs (per-tile maxima the clip-floor pass reduces,
- * 94 x 8 floats per clip).  The workspace needs no initialisation by the caller. */
+/* Bytes of device workspace a call with `batch` clips needs (per-tile {max, min} pairs the clip-floor pass reduces,
+ * 94 x 8 float pairs per clip).  The workspace needs no initialisation by the caller. */
 size_t b200mel_workspace_bytes(const b200mel_handle* h, int32_t batch);
 
 /* Whisper preset.
