@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import sys
@@ -602,7 +603,24 @@ def run_sweep(args) -> dict | None:
     chunk = args.chunk
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)                                     # Philox, a stream per rank
-    pool = 0.1 * torch.randn((chunk, 480000), generator=gen, device=dev, dtype=torch.float32)   # 7.9 GB at 4096 clips
+    pool = torch.randn((chunk, 480000), generator=gen, device=dev, dtype=torch.float32)   # 7.9 GB at 4096 clips
+    if args.sweep_pool == "noise":
+        pool.mul_(0.1)
+        pool_desc = "0.1 N(0,1)"
+    else:
+        # the bench's four signal classes in equal shares (signals.whisper_clip's formulas, evaluated on the device in
+        # slabs; clip i is class i % 4): the floor pass skips the first two classes and clamps most of the other two
+        t = torch.arange(480000, device=dev, dtype=torch.float64) / 16000.0
+        tone = (0.5 * torch.sin(2 * math.pi * 440.0 * t)).float()
+        chirp = (0.5 * torch.sin(2 * math.pi * (50.0 * t + 0.5 * (7900.0 - 50.0) / 30.0 * t * t))).float()
+        am = ((0.5 + 0.5 * torch.sin(2 * math.pi * 3.0 * t)) ** 4).float()
+        del t
+        pool[0::4].mul_(0.1)
+        pool[1::4].mul_(0.01).add_(tone)
+        pool[2::4].copy_(chirp.expand_as(pool[2::4]))
+        pool[3::4].mul_(0.3).mul_(am)
+        del tone, chirp, am
+        pool_desc = "the four signal classes of the bench in equal shares"
     ops.whisper_logmel(pool[:64], None)
     torch.cuda.synchronize()
     rows = []
@@ -641,7 +659,7 @@ def run_sweep(args) -> dict | None:
     for r in rows:
         r["hbm_frac_per_gpu"] = r["clips_per_s_median"] / world * BYTES_PER_CLIP / (peak * 1e9)
     return {"metric": METRIC, "mode": "sweep", "unit": UNIT, "n_gpus": world, "chunk_clips": chunk, "reps": args.sweep_reps,
-            "data": "synthetic (0.1 N(0,1) generated on the device, a Philox stream per rank)",
+            "data": f"synthetic ({pool_desc}, generated on the device, a Philox stream per rank)", "pool": args.sweep_pool,
             "timing": "CUDA events around the enqueue loop of one pass, max over ranks per pass; median and best of the passes",
             "partition": "contiguous shards (sharding.shard_range), no collective on the data path", "rows": rows}
 
@@ -655,6 +673,8 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch, if known (else null)")
+    ap.add_argument("--sweep-pool", choices=("mixed", "noise"), default="mixed",
+                    help="--sweep: the four bench classes in equal shares (default) or white noise only (nothing for the floor pass to do)")
     ap.add_argument("--sweep", action="store_true", help="1k..64k clips in --chunk-clip chunks from a device-resident pool")
     ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--sweep-reps", type=int, default=5)
