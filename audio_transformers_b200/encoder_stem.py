@@ -57,3 +57,39 @@ class B200WhisperEncoderStem(torch.nn.Module):
         if not input_features.is_cuda:
             raise RuntimeError("B200WhisperEncoderStem: input_features must be a CUDA tensor (there is no CPU path)")
         return ops.encoder_stem(input_features.float(), self.w1, self.bias1, self.w2, self.bias2, self.positions)
+
+
+def use_b200_stem(encoder) -> B200WhisperEncoderStem:
+    """Make a ``transformers`` ``WhisperEncoder`` run its first lines (HF:models/whisper/modeling_whisper.py:619-625:
+    conv1, GELU, conv2, GELU, permute, positions) on the tensor-core stem; the transformer layers and the final layer
+    norm (:628-645) stay the module's own.  For inference call sites of the reference (REF:whisper_finetune/
+    evaluate_simple.py:115-143, inference.py:154-170: ``model.whisper.generate`` / ``model(...)`` under
+    ``torch.no_grad()``): the stem has no backward, so a call that would need gradients raises instead of silently
+    training through a constant.  The weights are packed once, here; call again after loading new weights.
+    ``encoder.forward`` is replaced on the instance; ``encoder._b200_original_forward`` keeps the module's own.
+    """
+    from transformers.modeling_outputs import BaseModelOutput
+
+    dev = encoder.conv1.weight.device
+    if dev.type != "cuda":
+        raise RuntimeError("use_b200_stem: move the encoder to a CUDA device first (there is no CPU path)")
+    stem = B200WhisperEncoderStem.from_encoder(encoder).to(dev)
+    original = getattr(encoder, "_b200_original_forward", None) or encoder.forward
+    expected = encoder.config.max_source_positions * encoder.conv1.stride[0] * encoder.conv2.stride[0]
+
+    def forward(input_features, attention_mask=None, **kwargs):
+        if torch.is_grad_enabled() and (encoder.training or input_features.requires_grad):
+            raise NotImplementedError("the B200 encoder stem is inference only (no backward): wrap the call in "
+                                      "torch.no_grad() / model.eval(), or restore encoder._b200_original_forward")
+        if input_features.shape[-1] != expected:
+            raise ValueError(f"Whisper expects the mel input features to be of length {expected}, but found "
+                             f"{input_features.shape[-1]}. Make sure to pad the input mel features to {expected}.")
+        hidden = stem(input_features).to(encoder.layer_norm.weight.dtype)
+        for layer in encoder.layers:
+            out = layer(hidden, None)
+            hidden = out[0] if isinstance(out, tuple) else out
+        return BaseModelOutput(last_hidden_state=encoder.layer_norm(hidden))
+
+    encoder._b200_original_forward = original
+    encoder.forward = forward
+    return stem

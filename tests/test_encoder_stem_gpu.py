@@ -91,3 +91,47 @@ def test_stem_rejects_cpu_and_wrong_shapes():
         stem(torch.zeros(1, 80, 3000))
     with pytest.raises(RuntimeError):
         ops.encoder_stem(torch.zeros(1, 80, 2999, device="cuda"), stem.w1, stem.bias1, stem.w2, stem.bias2, stem.positions)
+
+
+def test_use_b200_stem_is_a_drop_in_for_the_reference_model():
+    """REF:whisper_finetune/evaluate_simple.py:115-143 with the encoder's stem swapped in place: the encoder output, the
+    emotion logits and the greedy token ids of a seeded random-init EmotionWhisperModel before and after
+    ``use_b200_stem(model.whisper.model.encoder)``."""
+    tr = pytest.importorskip("transformers")
+    from audio_transformers_b200.encoder_stem import use_b200_stem
+    from test_downstream_gpu import _reference_class, _restated_class
+    cls = _reference_class() or _restated_class()
+    torch.manual_seed(1234)
+    model = cls(tr.WhisperConfig(), num_emotions_classes=10).eval().cuda()
+    feats = _features(4, seed=21)
+    eos = model.config.eos_token_id
+
+    def run():
+        with torch.no_grad():
+            enc = model.whisper.model.encoder(feats).last_hidden_state
+            ids = model.whisper.generate(feats, max_new_tokens=40, eos_token_id=eos, pad_token_id=eos, do_sample=False,
+                                         no_repeat_ngram_size=3, repetition_penalty=1.15, length_penalty=-0.5,
+                                         forced_decoder_ids=None)
+            emo = model(input_features=feats, decoder_input_ids=ids)["emotion_logits"]
+        return enc, ids, emo
+
+    enc0, ids0, emo0 = run()
+    encoder = model.whisper.model.encoder
+    use_b200_stem(encoder)
+    enc1, ids1, emo1 = run()
+    rel = float((enc1 - enc0).norm() / enc0.norm())
+    n = min(ids0.shape[1], ids1.shape[1])
+    same = float((ids0[:, :n] == ids1[:, :n]).float().mean())
+    print(f"encoder output rel-fro {rel:.2e}; greedy ids equal {same:.3f} of {ids0.numel()} tokens; "
+          f"max |d emotion logit| {float((emo0 - emo1).abs().max()):.2e} (argmax equal: {bool(torch.equal(emo0.argmax(-1), emo1.argmax(-1)))})")
+    assert rel <= 2e-3
+    # BF16 operands move the encoder output by ~2e-4: a random-init decoder may flip a near-tie, a trained one does not sit
+    # on ties; the bound here is on how much may differ, the printed line says how much did
+    assert same >= 0.9
+    with pytest.raises(NotImplementedError):
+        encoder.train()
+        encoder(feats)
+    encoder.eval()
+    encoder.forward = encoder._b200_original_forward
+    with torch.no_grad():
+        assert torch.equal(encoder(feats).last_hidden_state, enc0)
