@@ -361,6 +361,20 @@ def encoder_stem_secondary(dev, dev_pool, peak_tflops) -> dict:
         ref = lib_stem(feats[0], torch.float32)
         got = stem(feats[0])
     out["max_abs_vs_torch_fp32"] = float((got - ref).abs().max())
+    # the whole encoder (BF16 weights) on the features, with the module's own stem and with
+    # use_b200_stem(encoder) swapped in
+    try:
+        from audio_transformers_b200.encoder_stem import use_b200_stem
+        enc16 = tr.WhisperModel(tr.WhisperConfig()).encoder.eval().to(dev).to(torch.bfloat16)
+        with torch.no_grad():
+            f16 = [f.to(torch.bfloat16) for f in feats]
+            ms_hf = timed(lambda i: enc16(f16[i % 2]), iters=5)
+            use_b200_stem(enc16)
+            ms_ours = timed(lambda i: enc16(feats[i % 2]), iters=5)
+        out["whole_encoder_bf16"] = {"hf_ms": ms_hf, "with_b200_stem_ms": ms_ours,
+                                     "note": "random-init whisper-tiny encoder, BF16 weights, 4 layers; the stem is the only part replaced"}
+    except Exception as exc:  # pragma: no cover
+        out["whole_encoder_bf16"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     return out
 
 
