@@ -5,7 +5,10 @@
 // of HF:feature_extraction_sequence_utils.py:263-278,327-332, up to the clip-wide floor (whisper_post.cuh).
 //
 // ONE 512-thread CTA per SM runs TWO independent halves (8 warps each, own audio / E / P buffers of 103 KB, own named
-// barrier and mbarrier): while one half waits at its barrier or on shared-memory loads the other computes.  A half
+// barrier and mbarriers): while one half waits at its barrier or on shared-memory loads the other computes.  Of a half's
+// two phase boundaries one is a block barrier (E complete before pass 2) and the other an mbarrier with one arrival per
+// warp ("phase B is over"), which a warp that starts with pass 1 only waits for when it has its DFT in registers and
+// wants to store it: the warps with little pass-2 work run ahead and carry more of the mel stage instead.  A half
 // works on 32-frame tiles; every FP32 value is a packed float2 holding the same quantity of two frames:
 //   pass 1   a warp is 8 frame pairs x 4 residue classes: windowed real 25-point DFTs (Good-Thomas 16 x 25);
 //   pass 2   the 16-point DFT is the same code for every k2 (no twiddles), so a warp takes 16 columns x 2 tasks;
@@ -15,6 +18,7 @@
 constexpr int V_TILE = 32, V_WARPS = 8;                                          // per half: 8 warps, one 32-frame tile in flight
 constexpr int V_HALVES = 2, V_HALF_THREADS = V_WARPS * 32, V_THREADS = V_HALVES * V_HALF_THREADS;
 constexpr int V_TILES_PER_CLIP = (W_NFRAME + V_TILE - 1) / V_TILE;               // 94
+constexpr int V_MEL_NS = 16, V_MEL_S6 = 5;                                       // mel shares in all / of warp 6 (v_mel_phase)
 constexpr int V_ROWS = ((V_TILE - 1) * W_HOP + W_NFFT + W_HOP - 1) / W_HOP;      // 34
 constexpr int V_COLS = V_TILE / 2;                                               // 16 float2 columns
 constexpr int V_SM_AUDIO = ((V_ROWS * W_PITCH + 31) / 32) * 32;                  // floats
@@ -95,10 +99,11 @@ __device__ __forceinline__ void v_stage_generic(const WTile& t, float* __restric
   }
 }
 
-// pass 1: windowed real 25-point DFT of residue class a for one frame pair per lane (E layout: 16 columns per row)
-__device__ __forceinline__ void v_pass1(int a, const float* __restrict__ audio_lane, float2* __restrict__ e_dst,
-                                        const int* __restrict__ s_off, const float* __restrict__ s_win) {
-  float2 x[25], o[25];
+// pass 1: windowed real 25-point DFT of residue class a for one frame pair per lane (E layout: 16 columns per row).
+// Loads + butterflies and the stores are separate so that a warp can compute before E is free (v_run).
+__device__ __forceinline__ void v_pass1_compute(int a, const float* __restrict__ audio_lane, const int* __restrict__ s_off,
+                                                const float* __restrict__ s_win, float2 (&o)[25]) {
+  float2 x[25];
   int off[28];
   float w[28];
   const int4* off4 = reinterpret_cast<const int4*>(s_off + a * 28);
@@ -119,9 +124,17 @@ __device__ __forceinline__ void v_pass1(int a, const float* __restrict__ audio_l
     x[b] = make_float2(p[0], p[W_LANE2]);
   }
   b2::real_dft25(x, w, o);
+}
+__device__ __forceinline__ void v_pass1_store(float2* __restrict__ e_dst, const float2 (&o)[25]) {
   e_dst[0] = o[0];
 #pragma unroll
   for (int c = 1; c < 25; ++c) e_dst[(c + 1) * V_COLS] = o[c];
+}
+__device__ __forceinline__ void v_pass1(int a, const float* __restrict__ audio_lane, float2* __restrict__ e_dst,
+                                        const int* __restrict__ s_off, const float* __restrict__ s_win) {
+  float2 o[25];
+  v_pass1_compute(a, audio_lane, s_off, s_win, o);
+  v_pass1_store(e_dst, o);
 }
 
 // pass 2 for one (k2, column) per lane; k2 >= 1
@@ -194,9 +207,27 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
   const float* pl = reinterpret_cast<const float*>(s_p) + 2 * col + half;
   float* out_col = out + (size_t)clip * (W_NMEL * W_NFRAME) + frame;
   float emax = 0.0f, emin = 3.0e38f;
-#define V_MEL_CASE(w) case w: v_mel_share<2 * w, 16>(pl, out_col, valid, emax, emin); v_mel_share<2 * w + 1, 16>(pl, out_col, valid, emax, emin); break;
-  switch (warp) { V_MEL_CASE(0) V_MEL_CASE(1) V_MEL_CASE(2) V_MEL_CASE(3) V_MEL_CASE(4) V_MEL_CASE(5) V_MEL_CASE(6) default: V_MEL_CASE(7) }
-#undef V_MEL_CASE
+  // The 80 filters are cut into V_MEL_NS shares of equal cost (w_mel_first).  Warps 0..5 carry a full pass-2 task each and
+  // take ONE share; warp 6 (half a pass-2 task) takes V_MEL_S6 and warp 7 (none: it stages and draws) the rest -- those
+  // two reach the end of phase B early, start their pass-1 task before the others have left pass 2 (v_run) and so have
+  // the time: measured at batch 512, kernel 0.494 ms with two shares per warp, 0.480 (2,..,2,4,5), 0.470 (2,..,2,7,8),
+  // 0.468 with this split (1,..,1,5,5), 0.475 (1,..,1,7,7).
+#define V_MS(s) if constexpr ((s) < V_MEL_NS) v_mel_share<((s) < V_MEL_NS ? (s) : 0), V_MEL_NS>(pl, out_col, valid, emax, emin);
+#define V_M6(k) if constexpr ((k) < V_MEL_S6) { V_MS(6 + (k)) }
+#define V_M7(k) V_MS(6 + V_MEL_S6 + (k))
+  switch (warp) {
+    case 0: V_MS(0) break;
+    case 1: V_MS(1) break;
+    case 2: V_MS(2) break;
+    case 3: V_MS(3) break;
+    case 4: V_MS(4) break;
+    case 5: V_MS(5) break;
+    case 6: V_M6(0) V_M6(1) V_M6(2) V_M6(3) V_M6(4) V_M6(5) V_M6(6) V_M6(7) break;
+    default: V_M7(0) V_M7(1) V_M7(2) V_M7(3) V_M7(4) V_M7(5) V_M7(6) V_M7(7) break;
+  }
+#undef V_MS
+#undef V_M6
+#undef V_M7
   if (!valid) { emax = 0.0f; emin = 3.0e38f; }
   // energies are >= +0, so their bit patterns order like the values: one REDUX each instead of five shuffle rounds
   emax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(emax)));
@@ -210,10 +241,11 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
 #ifndef V_ROTATE
 #define V_ROTATE 0      // 1: the second half shifts its pass-2 roles by two warps (no measurable effect)
 #endif
-// which warps run their mel share before their pass-1 task: opposite choices in the two halves (the halves then tend to
-// be in complementary parts of phase A: 1.00 M vs 0.965 M clips/s with the same choice in both)
+// which warps run their mel share before their pass-1 task: three of warps 0..5, the other three in the other half (the
+// halves then tend to be in complementary parts of phase A: 1.00 M vs 0.965 M clips/s with the same choice in both);
+// warps 6 and 7 always start with pass 1, which they may begin before the phase barrier (see v_run)
 #ifndef V_MEL_FIRST
-#define V_MEL_FIRST(w) ((((w) >> 2) & 1) ^ half)
+#define V_MEL_FIRST(w) ((w) < 6 && ((((w) >= 3) ? 1 : 0) ^ half) == 0)
 #endif
 
 // One 512-thread CTA per SM runs TWO independent halves (8 warps each, own audio / E / P buffers, own named barrier
@@ -294,20 +326,29 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
   bool cur_tma = false;
   if (cur.x < ntiles) cur_tma = stage(unpack(cur));
   int prev_clip = -1, prev_f0 = 0;
+  // "every warp of the half has left phase B": an mbarrier with one arrival per warp instead of a block barrier, so that a
+  // warp may load and transform its pass-1 inputs (the audio tile is complete once the TMA barrier says so) while
+  // slower warps are still in pass 2; only its E stores and the mel stage wait
+  unsigned long long* s_done = reinterpret_cast<unsigned long long*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB) + 12 + half;
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s_done);
 
 #pragma unroll 1
   for (int it = 0;; ++it) {
     const bool have = cur.x < ntiles;
     if (have && cur_tma) { mbar_wait(s_bar, tma_parity); tma_parity ^= 1u; }
-    half_sync();                           // audio(tile) visible; P(previous tile) complete; E is free
-
-    // ---- phase A: mel(previous tile) + pass 1(this tile) ----------------------------------------------
+    // one call site per stage (the instruction cache does not hold the tile loop twice)
+    const bool early = have && cur_tma && !mel_first;
+    if (!early) mbar_wait(s_done, (unsigned)(it & 1));       // audio (ordinary stores) visible; P complete; E free
 #pragma unroll 1
     for (int step = 0; step < 2; ++step) {
       if ((step == 0) == mel_first) {
         if (prev_clip >= 0) v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, tile_max);
       } else if (have) {
-        v_pass1(p1_a, audio_lane, p1_dst, s_off, s_win);
+        float2 o[25];
+        v_pass1_compute(p1_a, audio_lane, s_off, s_win, o);
+        if (early) mbar_wait(s_done, (unsigned)(it & 1));    // P(previous tile) complete; E is free
+        v_pass1_store(p1_dst, o);
       }
     }
     if (!have) break;
@@ -324,6 +365,8 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
     prev_clip = cur.y;
     prev_f0 = cur.z;
     cur = next;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s_done);
   }
 }
 
@@ -338,7 +381,11 @@ whisper_logmel_kernel32(const __grid_constant__ CUtensorMap tmap, int use_tma,
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + V_HALVES * V_HALF_FLOATS + W_SM_TAB);
     int* s_ctl = reinterpret_cast<int*>(s_bar) + 4;
     for (int i = threadIdx.x; i < 16 * 28; i += V_THREADS) { s_off[i] = c_wp1_off[i]; s_win[i] = c_wp1_win[i]; }
-    if (threadIdx.x == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); fence_proxy_async(); s_ctl[0] = 0; }
+    if (threadIdx.x == 0) {
+      mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1);
+      mbar_init(s_bar + 12, V_WARPS); mbar_init(s_bar + 13, V_WARPS);
+      fence_proxy_async(); s_ctl[0] = 0;
+    }
   }
   __syncthreads();
   // The kernel is launched with programmatic stream serialisation: it may become resident and run its prologue
