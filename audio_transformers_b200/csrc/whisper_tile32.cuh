@@ -18,7 +18,13 @@
 constexpr int V_TILE = 32, V_WARPS = 8;                                          // per half: 8 warps, one 32-frame tile in flight
 constexpr int V_HALVES = 2, V_HALF_THREADS = V_WARPS * 32, V_THREADS = V_HALVES * V_HALF_THREADS;
 constexpr int V_TILES_PER_CLIP = (W_NFRAME + V_TILE - 1) / V_TILE;               // 94
-constexpr int V_MEL_NS = 16, V_MEL_S6 = 5;                                       // mel shares in all / of warp 6 (v_mel_phase)
+#ifndef V_NS
+#define V_NS 16
+#endif
+#ifndef V_S6
+#define V_S6 5
+#endif
+constexpr int V_MEL_NS = V_NS, V_MEL_S6 = V_S6;                                  // mel shares in all / of the role with the real pass-2 task (v_mel_phase)
 constexpr int V_ROWS = ((V_TILE - 1) * W_HOP + W_NFFT + W_HOP - 1) / W_HOP;      // 34
 constexpr int V_COLS = V_TILE / 2;                                               // 16 float2 columns
 constexpr int V_SM_AUDIO = ((V_ROWS * W_PITCH + 31) / 32) * 32;                  // floats
@@ -198,7 +204,7 @@ __device__ __forceinline__ void v_mel_share(const float* __restrict__ p_lane, fl
   v_mel_filters<FB, FE, BLO, NB>(pb, out_col, valid, emax, emin);
 }
 
-__device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0, const float2* __restrict__ s_p,
+__device__ __forceinline__ void v_mel_phase(int role, int warp, int lane, int clip, int f0, const float2* __restrict__ s_p,
                                             float* __restrict__ out, float2* __restrict__ tile_max) {
   // lane l < 16: first frame of column l; lane l >= 16: second frame (8 frames later) of column l - 16
   const int col = lane & 15, half = lane >> 4;
@@ -215,7 +221,7 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
 #define V_MS(s) if constexpr ((s) < V_MEL_NS) v_mel_share<((s) < V_MEL_NS ? (s) : 0), V_MEL_NS>(pl, out_col, valid, emax, emin);
 #define V_M6(k) if constexpr ((k) < V_MEL_S6) { V_MS(6 + (k)) }
 #define V_M7(k) V_MS(6 + V_MEL_S6 + (k))
-  switch (warp) {
+  switch (role) {
     case 0: V_MS(0) break;
     case 1: V_MS(1) break;
     case 2: V_MS(2) break;
@@ -239,7 +245,8 @@ __device__ __forceinline__ void v_mel_phase(int warp, int lane, int clip, int f0
 #define V_L2_PREFETCH 1
 #endif
 #ifndef V_ROTATE
-#define V_ROTATE 0      // 1: the second half shifts its pass-2 roles by two warps (no measurable effect)
+#define V_ROTATE 1      // the second half shifts its roles by two warps: its two light-pass-2 / heavy-mel warps then sit on the
+                        // schedulers that carry four ordinary warps (64-clip step 78.1 -> 76.4 us)
 #endif
 // which warps run their mel share before their pass-1 task: three of warps 0..5, the other three in the other half (the
 // halves then tend to be in complementary parts of phase A: 1.00 M vs 0.965 M clips/s with the same choice in both);
@@ -280,8 +287,8 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
   const int p2_warp = (warp + (V_ROTATE ? 2 * half : 0)) & 7;
   const int p2_col = lane & 15;
   const int p2_k2 = 1 + 2 * p2_warp + (lane >> 4);
-  const bool mel_first = V_MEL_FIRST(warp);
-  constexpr int STAGE_TID = 7 * 32;
+  const bool mel_first = V_MEL_FIRST(p2_warp);
+  const int STAGE_TID = ((7 - (V_ROTATE ? 2 * half : 0)) & 7) * 32;      // lane 0 of the warp whose role has no pass-2 task
 
   // Draw tiles from the shared counter until one has audio in it (tiles of pure zero padding only get their maximum
   // recorded); for that one, pull its TMA box into L2 already.  Called by ONE thread of the half, which publishes
@@ -343,7 +350,7 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
 #pragma unroll 1
     for (int step = 0; step < 2; ++step) {
       if ((step == 0) == mel_first) {
-        if (prev_clip >= 0) v_mel_phase(warp, lane, prev_clip, prev_f0, s_p, out, tile_max);
+        if (prev_clip >= 0) v_mel_phase(p2_warp, warp, lane, prev_clip, prev_f0, s_p, out, tile_max);
       } else if (have) {
         float2 o[25];
         v_pass1_compute(p1_a, audio_lane, s_off, s_win, o);
