@@ -218,6 +218,8 @@ __device__ __forceinline__ void v_mel_phase(int role, int warp, int lane, int cl
   // two reach the end of phase B early, start their pass-1 task before the others have left pass 2 (v_run) and so have
   // the time: measured at batch 512, kernel 0.494 ms with two shares per warp, 0.480 (2,..,2,4,5), 0.470 (2,..,2,7,8),
   // 0.468 with this split (1,..,1,5,5), 0.475 (1,..,1,7,7).
+  static_assert(V_MEL_S6 >= 1 && V_MEL_S6 <= 8 && V_MEL_NS > 6 + V_MEL_S6 && V_MEL_NS <= 6 + V_MEL_S6 + 8,
+                "every share must belong to exactly one role: six single shares, V_MEL_S6 for role 6, at most eight for role 7");
 #define V_MS(s) if constexpr ((s) < V_MEL_NS) v_mel_share<((s) < V_MEL_NS ? (s) : 0), V_MEL_NS>(pl, out_col, valid, emax, emin);
 #define V_M6(k) if constexpr ((k) < V_MEL_S6) { V_MS(6 + (k)) }
 #define V_M7(k) V_MS(6 + V_MEL_S6 + (k))
