@@ -135,3 +135,25 @@ def test_use_b200_stem_is_a_drop_in_for_the_reference_model():
     encoder.forward = encoder._b200_original_forward
     with torch.no_grad():
         assert torch.equal(encoder(feats).last_hidden_state, enc0)
+
+
+def test_stem_empty_batch_and_graph_replay():
+    """Batch 0 returns an empty tensor without a launch; the call is capturable (no allocation by the library, no sync)
+    and a replay reproduces the eager result bit for bit."""
+    from audio_transformers_b200 import B200WhisperEncoderStem
+    enc = _encoder()
+    stem = B200WhisperEncoderStem.from_encoder(enc).cuda()
+    assert stem(torch.zeros(0, 80, 3000, device="cuda")).shape == (0, 1500, 384)
+    feats = _features(3, seed=13)
+    eager = stem(feats).clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        stem(feats)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = stem(feats)
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out, eager)

@@ -394,3 +394,22 @@ def test_processor_audio_path_vs_live_hf():
     assert both["labels"] == [[7, 8, 9]] and torch.equal(both["input_features"].squeeze(0), a)
     assert torch.equal(proc.feature_extractor(audio, sampling_rate=16000, return_tensors="pt").input_features.squeeze(0), a)
     assert a.to("cuda") is a                          # REF:whisper_finetune/inference.py:154 `.to(device)` is a no-op
+
+
+def test_two_streams_interleaved_match_serial(ops):
+    """The handle is immutable and the workspace is per (stream, batch): calls enqueued alternately on two streams, with
+    different batches in flight at once, give the bits of the same calls run one after the other."""
+    waves = [torch.from_numpy(signals.whisper_batch(n, seed=40 + i)).cuda() for i, n in enumerate((5, 9, 5, 12, 9, 3))]
+    lens = [torch.tensor([int(v) for v in signals.ragged_lengths(w.shape[0], seed=50 + i)], dtype=torch.int32).cuda()
+            for i, w in enumerate(waves)]
+    serial = [ops.whisper_logmel(w, l).clone() for w, l in zip(waves, lens)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [None] * len(waves)
+    for rep in range(3):
+        for i, (w, l) in enumerate(zip(waves, lens)):
+            with torch.cuda.stream(streams[i % 2]):
+                outs[i] = ops.whisper_logmel(w, l)
+    torch.cuda.synchronize()
+    for a, b in zip(serial, outs):
+        assert torch.equal(a, b)
