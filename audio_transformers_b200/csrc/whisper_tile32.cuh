@@ -283,10 +283,12 @@ __device__ __forceinline__ void v_run(const CUtensorMap* tmap, int use_tma, cons
   const int p1_a = 4 * (warp & 3) + (lane >> 3);
   const float* audio_lane = s_audio + (16 * (warp >> 2) + (lane & 7)) * W_PITCH;
   float2* p1_dst = s_e + p1_a * V_EBLK + 8 * (warp >> 2) + (lane & 7);
-  // pass-2 role: warps 0..5 take tasks k2 = 1 + 2 warp + lane / 16, warp 6 the real task k2 = 0 (lanes 0..15), warp 7 none.
-  // The second half rotates the roles by two warps: its light warps (real task, idle) then sit on the schedulers that
-  // carry two full tasks of the first half.
-  const int p2_warp = (warp + (V_ROTATE ? 2 * half : 0)) & 7;
+  // The ROLE of a warp decides its pass-2 task, its mel shares and whether it stages: roles 0..5 take the tasks
+  // k2 = 1 + 2 role + lane / 16 and one mel share each; role 6 the real task k2 = 0 (lanes 0..15) and V_MEL_S6 shares;
+  // role 7 no pass-2 task (it issues the copies and draws tiles) and the remaining shares.  Roles 6 and 7 are the ones
+  // that run ahead into the next tile's pass 1.  In the first half role = warp; the second half rotates by two warps, so
+  // that its roles 6 and 7 (warps 4 and 5) sit on other schedulers than the first half's.
+  const int p2_warp = (warp + (V_ROTATE ? 2 * half : 0)) & 7;                 // the role
   const int p2_col = lane & 15;
   const int p2_k2 = 1 + 2 * p2_warp + (lane >> 4);
   const bool mel_first = V_MEL_FIRST(p2_warp);
